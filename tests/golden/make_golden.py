@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference; the GPU box has no
+reference tree, it only reads the .npz files this script wrote):
+
+    python tests/golden/make_golden.py
+
+* ``embedding_help_functions`` is imported as-is (behind a stub for the unused
+  ``matplotlib`` import, ehf:11).
+* ``func_MProduct`` / ``func_MProduct_dense`` / ``create_matrix_M`` live in
+  scripts that execute at import (SBM_our.py needs ``dynamicgem``), so their
+  source lines are read from /root/reference at run time and exec()'d -- the
+  text is never stored in this repo.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch as t
+
+warnings.filterwarnings("ignore")
+REF = "/root/reference/TensorGCN-master"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+for m in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(m, types.ModuleType(m))
+sys.path.insert(0, REF)
+import embedding_help_functions as ehf  # noqa: E402
+
+
+def load_ref_functions(no_diag):
+    src = open(os.path.join(REF, "SBM_our.py")).read().split("\n")
+    a = [i for i, l in enumerate(src) if l.startswith("def func_MProduct(")][0]
+    b = [i for i, l in enumerate(src) if l.startswith("def load_data(")][0]
+    ns = {"t": t, "np": np, "no_diag": no_diag}
+    exec("\n".join(src[a:b]), ns)
+    return ns
+
+
+def ref_M_normalised(T, no_diag):
+    """read_data.py:56-62 executed from the reference text."""
+    src = open(os.path.join(REF, "read_data.py")).read().split("\n")
+    a = [i for i, l in enumerate(src) if l.startswith("#Create M")][0]
+    ns = {"np": np, "torch": t, "T": T, "no_diag": no_diag}
+    exec("\n".join(src[a + 1:a + 8]), ns)
+    return ns["M"]
+
+
+def random_coo(T, N, density, seed, symmetric_diag=True):
+    g = t.Generator().manual_seed(seed)
+    dense = (t.rand(T, N, N, generator=g) < density).double() * (t.rand(T, N, N, generator=g).double() + 0.1)
+    if symmetric_diag:
+        dense = (dense + dense.transpose(1, 2)) / 2
+        dense = dense + t.eye(N, dtype=t.float64)[None]
+        d = dense.sum(2)
+        dense = dense / t.sqrt(d)[:, :, None] / t.sqrt(d)[:, None, :]
+    return dense.to_sparse().coalesce()
+
+
+def slice_list(C, T):
+    # experiment_bitcoin_our.py:53-56 (legacy ctor keeps the fp64 values)
+    out = []
+    for j in range(T):
+        idx = C._indices()[0] == j
+        out.append(t.sparse.FloatTensor(C._indices()[1:3, idx], C._values()[idx]))
+    return out
+
+
+def gen_mproduct():
+    cases = {}
+    for name, (T, N, dens, b, norm, seed) in {
+        "t8n50b3": (8, 50, 0.05, 3, False, 1),
+        "t8n50b3norm": (8, 50, 0.05, 3, True, 2),
+        "t12n33b20": (12, 33, 0.10, 20, False, 3),   # band wider than T
+        "t5n17b1": (5, 17, 0.20, 1, False, 4),       # M = I
+        "t9n40raw": (9, 40, 0.08, 4, False, 5),      # unsymmetric, no diagonal
+    }.items():
+        ns = load_ref_functions(b)
+        C = random_coo(T, N, dens, seed, symmetric_diag=(name != "t9n40raw"))
+        M = ref_M_normalised(T, b) if norm else ns["create_matrix_M"](T, b)
+        out = ns["func_MProduct"](C, M)
+        outd = ns["func_MProduct_dense"](C, M).coalesce()
+        assert t.equal(out._indices(), outd._indices())
+        cases[name + "_in_idx"] = C._indices().numpy()
+        cases[name + "_in_val"] = C._values().numpy()
+        cases[name + "_shape"] = np.array([T, N, N])
+        cases[name + "_b"] = np.array(b)
+        cases[name + "_M"] = M.numpy()
+        cases[name + "_out_idx"] = out._indices().numpy()
+        cases[name + "_out_val"] = out._values().numpy()
+        cases[name + "_outd_val"] = outd._values().numpy()
+    np.savez_compressed(os.path.join(OUT, "mproduct.npz"), **cases)
+    print("mproduct.npz", len(cases))
+
+
+def gen_chess():
+    """Real-shape input: first 6 monthly slices of the shipped KONECT chess
+    file (whitespace separated, `%` comments), restricted to the 600 busiest
+    players so the fixture stays small; symmetrised + normalised the reference
+    way, then func_MProduct with b=3."""
+    raw = np.loadtxt(os.path.join(REF, "data/chess/out.chess.csv"), comments="%")
+    dates = np.unique(raw[:, 3])
+    keep = np.isin(raw[:, 3], dates[:40])
+    raw = raw[keep]
+    # the 6 busiest months of the first 40
+    cnt = np.array([(raw[:, 3] == d).sum() for d in dates[:40]])
+    months = np.sort(np.argsort(-cnt)[:6])
+    ids, c = np.unique(np.concatenate([raw[:, 0], raw[:, 1]]), return_counts=True)
+    top = ids[np.argsort(-c)[:600]]
+    remap = {int(v): i for i, v in enumerate(np.sort(top))}
+    T, N = 6, 600
+    dense = t.zeros(T, N, N, dtype=t.float64)
+    for k, mth in enumerate(months):
+        rows = raw[raw[:, 3] == dates[mth]]
+        for a, b_, w, _ in rows:
+            if int(a) in remap and int(b_) in remap and a != b_:
+                dense[k, remap[int(a)], remap[int(b_)]] = 1.0
+    dense = (dense + dense.transpose(1, 2)) / 2 + t.eye(N, dtype=t.float64)[None]
+    d = dense.sum(2)
+    dense = dense / t.sqrt(d)[:, :, None] / t.sqrt(d)[:, None, :]
+    C = dense.to_sparse().coalesce()
+    ns = load_ref_functions(3)
+    M = ns["create_matrix_M"](T, 3)
+    out = ns["func_MProduct"](C, M)
+    np.savez_compressed(
+        os.path.join(OUT, "chess6.npz"),
+        in_idx=C._indices().numpy().astype(np.int32), in_val=C._values().numpy(),
+        shape=np.array([T, N, N]), b=np.array(3), M=M.numpy(),
+        out_idx=out._indices().numpy().astype(np.int32), out_val=out._values().numpy())
+    print("chess6.npz nnz in/out", C._nnz(), out._nnz())
+
+
+def grads(mod, out, dOut, names):
+    for p in mod.parameters():
+        p.grad = None
+    out.backward(dOut)
+    return {n: getattr(mod, n).grad.detach().numpy().copy() for n in names}
+
+
+def gen_models():
+    ns = load_ref_functions(3)
+    T, N, F0, E = 6, 40, 2, 90
+    C = random_coo(T, N, 0.08, 11)
+    M = ns["create_matrix_M"](T, 3)
+    Ct = ns["func_MProduct"](C, M)
+    At = slice_list(Ct, T)
+    A = slice_list(C, T)
+    g = t.Generator().manual_seed(12)
+    X = t.rand(T, N, F0, generator=g, dtype=t.float64)
+    X2 = t.rand(T, N, F0, generator=g, dtype=t.float64)
+    edges = t.stack([t.randint(0, T, (E,), generator=g), t.randint(0, N, (E,), generator=g),
+                     t.randint(0, N, (E,), generator=g)])
+    edges = edges[:, t.argsort(edges[0], stable=True)]
+    edges2 = edges[:, t.randperm(E, generator=g)[:50]]
+    d = {"C_idx": C._indices().numpy(), "C_val": C._values().numpy(),
+         "Ct_idx": Ct._indices().numpy(), "Ct_val": Ct._values().numpy(),
+         "M": M.numpy(), "X": X.numpy(), "X2": X2.numpy(),
+         "edges": edges.numpy(), "edges2": edges2.numpy(), "TN": np.array([T, N])}
+
+    # 1-layer (ehf:156-234) -- cached and fresh-input forward, gradients
+    t.manual_seed(100)
+    m = ehf.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=True, use_Minv=False)
+    dOut = t.randn(E, 2, generator=g)
+    out = m()
+    d["gcn1_W"], d["gcn1_U"] = m.W.detach().numpy().copy(), m.U.detach().numpy().copy()
+    d["gcn1_AtXt"] = m.AtXt.numpy()
+    d["gcn1_out"], d["gcn1_dOut"] = out.detach().numpy(), dOut.numpy()
+    for k, v in grads(m, out, dOut, ["W", "U"]).items():
+        d["gcn1_d" + k] = v
+    with t.no_grad():
+        d["gcn1_out_fresh"] = m(At, X2, edges2).numpy()
+
+    # 2-layer variants (ehf:236-357)
+    for tag, kw in {
+        "relu": dict(nonlin2="relu"),
+        "leaky": dict(nonlin2="leaky"),
+        "selu": dict(nonlin2="selu"),
+        "selu_m2": dict(nonlin2="selu", apply_M_twice=True),
+        "relu_m3": dict(nonlin2="relu", apply_M_twice=True, apply_M_three_times=True),
+    }.items():
+        t.manual_seed(200)
+        m = ehf.EmbeddingGCN2(At, X, edges, M, hidden_feat=[6, 6, 2], condensed_W=True, use_Minv=False, **kw)
+        out = m()
+        p = "gcn2_" + tag + "_"
+        d[p + "W1"], d[p + "W2"], d[p + "U"] = (x.detach().numpy().copy() for x in (m.W1, m.W2, m.U))
+        d[p + "out"] = out.detach().numpy()
+        for k, v in grads(m, out, dOut, ["W1", "W2", "U"]).items():
+            d[p + "d" + k] = v
+        with t.no_grad():
+            d[p + "out_fresh"] = m(At, X2, edges2).numpy()
+
+    # static baseline (ehf:425-497), 1 and 2 layers
+    for tag, hf in {"kw1": [6, 2], "kw2": [6, 6, 2]}.items():
+        t.manual_seed(300)
+        m = ehf.EmbeddingKWGCN(A, X, edges, hidden_feat=hf, nonlin2="leaky")
+        out = m()
+        p = tag + "_"
+        names = ["W1", "U"] + (["W2"] if len(hf) == 3 else [])
+        for n in names:
+            d[p + n] = getattr(m, n).detach().numpy().copy()
+        d[p + "out"] = out.detach().numpy()
+        for k, v in grads(m, out, dOut, names).items():
+            d[p + "d" + k] = v
+        with t.no_grad():
+            d[p + "out_fresh"] = m(A, X2, edges2).numpy()
+
+    # wide-feature layer: F 32 -> 48 -> 16 -> 3, gradient w.r.t. the layer-2 input
+    # is exercised through W1 (chain through compute_AtXt with grad, ehf:343)
+    t.manual_seed(400)
+    Xw = t.rand(T, N, 32, generator=g, dtype=t.float64)
+    m = ehf.EmbeddingGCN2(At, Xw, edges, M, hidden_feat=[48, 16, 3], condensed_W=True, use_Minv=False,
+                          apply_M_twice=True, nonlin2="relu")
+    # randn weights at F=32..48 blow the activations up; scale them like the tests will
+    with t.no_grad():
+        m.W1 *= 0.2
+        m.W2 *= 0.2
+    dOut3 = t.randn(E, 3, generator=g)
+    out = m()
+    d["wide_X"] = Xw.numpy()
+    d["wide_W1"], d["wide_W2"], d["wide_U"] = (x.detach().numpy().copy() for x in (m.W1, m.W2, m.U))
+    d["wide_out"], d["wide_dOut"] = out.detach().numpy(), dOut3.numpy()
+    for k, v in grads(m, out, dOut3, ["W1", "W2", "U"]).items():
+        d["wide_d" + k] = v
+    np.savez_compressed(os.path.join(OUT, "models.npz"), **d)
+    print("models.npz", len(d))
+
+
+if __name__ == "__main__":
+    gen_mproduct()
+    gen_chess()
+    gen_models()

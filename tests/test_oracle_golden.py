@@ -1,0 +1,142 @@
+"""Pin the oracle against outputs of the unmodified reference (tests/golden/*.npz,
+written by tests/golden/make_golden.py in the build container)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import MPRODUCT_CASES
+
+
+@pytest.mark.parametrize("name", MPRODUCT_CASES)
+def test_func_mproduct_matches_reference(golden_mproduct, name):
+    g = golden_mproduct
+    idx, val = oracle.func_MProduct(g[name + "_in_idx"], g[name + "_in_val"], tuple(g[name + "_shape"]),
+                                    g[name + "_M"], no_diag=int(g[name + "_b"]))
+    assert idx.dtype == np.int64
+    assert np.array_equal(idx, g[name + "_out_idx"])          # bit-exact indices
+    np.testing.assert_allclose(val, g[name + "_out_val"], rtol=1e-14, atol=0)
+    idx_d, val_d = oracle.func_MProduct_dense(g[name + "_in_idx"], g[name + "_in_val"],
+                                              tuple(g[name + "_shape"]), g[name + "_M"])
+    assert np.array_equal(idx_d, g[name + "_out_idx"])        # a2 == a3 (invariant 1)
+    np.testing.assert_allclose(val_d, g[name + "_outd_val"], rtol=1e-14, atol=0)
+
+
+def test_func_mproduct_chess(golden_chess):
+    g = golden_chess
+    idx, val = oracle.func_MProduct(g["in_idx"].astype(np.int64), g["in_val"], tuple(g["shape"]), g["M"], no_diag=3)
+    assert np.array_equal(idx, g["out_idx"].astype(np.int64))
+    np.testing.assert_allclose(val, g["out_val"], rtol=1e-14, atol=0)
+
+
+def test_create_matrix_M(golden_mproduct):
+    g = golden_mproduct
+    assert np.array_equal(oracle.create_matrix_M(8, 3).numpy(), g["t8n50b3_M"])
+    assert np.array_equal(oracle.create_matrix_M(12, 20).numpy(), g["t12n33b20_M"])
+    np.testing.assert_allclose(oracle.create_matrix_M(8, 3, normalize=True).numpy(), g["t8n50b3norm_M"],
+                               rtol=1e-15)
+
+
+def _inputs(g):
+    T, N = (int(x) for x in g["TN"])
+    M = torch.from_numpy(g["M"])
+    At = oracle.split_slices(g["Ct_idx"], g["Ct_val"], T, N)
+    A = oracle.split_slices(g["C_idx"], g["C_val"], T, N)
+    X, X2 = torch.from_numpy(g["X"]), torch.from_numpy(g["X2"])
+    edges, edges2 = torch.from_numpy(g["edges"]), torch.from_numpy(g["edges2"])
+    return T, N, M, At, A, X, X2, edges, edges2
+
+
+def _eq(a, b):
+    # same ATen kernels, same order => the restatement must agree to the last bit
+    # (allow 1 ulp-ish slack for threaded reductions)
+    np.testing.assert_allclose(a.detach().numpy() if torch.is_tensor(a) else a, b, rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("as_reference", [True, False])
+def test_gcn1(golden_models, as_reference):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    m = oracle.OracleGCN(At, X, edges, M, torch.from_numpy(g["gcn1_W"]), torch.from_numpy(g["gcn1_U"]), as_reference)
+    _eq(m.AtXt, g["gcn1_AtXt"])
+    out = m()
+    _eq(out, g["gcn1_out"])
+    out.backward(torch.from_numpy(g["gcn1_dOut"]))
+    _eq(m.W.grad, g["gcn1_dW"])
+    _eq(m.U.grad, g["gcn1_dU"])
+    with torch.no_grad():
+        _eq(m(At, X2, edges2), g["gcn1_out_fresh"])
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("relu", dict(nonlin2="relu")), ("leaky", dict(nonlin2="leaky")), ("selu", dict(nonlin2="selu")),
+    ("selu_m2", dict(nonlin2="selu", apply_M_twice=True)),
+    ("relu_m3", dict(nonlin2="relu", apply_M_twice=True, apply_M_three_times=True))])
+def test_gcn2(golden_models, tag, kw):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    p = "gcn2_" + tag + "_"
+    m = oracle.OracleGCN2(At, X, edges, M, *(torch.from_numpy(g[p + n]) for n in ("W1", "W2", "U")), **kw)
+    out = m()
+    _eq(out, g[p + "out"])
+    out.backward(torch.from_numpy(g["gcn1_dOut"]))
+    for n in ("W1", "W2", "U"):
+        _eq(getattr(m, n).grad, g[p + "d" + n])
+    with torch.no_grad():
+        _eq(m(At, X2, edges2), g[p + "out_fresh"])
+
+
+@pytest.mark.parametrize("tag", ["kw1", "kw2"])
+def test_kwgcn(golden_models, tag):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    p = tag + "_"
+    W2 = torch.from_numpy(g[p + "W2"]) if tag == "kw2" else None
+    m = oracle.OracleKWGCN(A, X, edges, torch.from_numpy(g[p + "W1"]), torch.from_numpy(g[p + "U"]), W2, "leaky")
+    out = m()
+    _eq(out, g[p + "out"])
+    out.backward(torch.from_numpy(g["gcn1_dOut"]))
+    for n in ["W1", "U"] + (["W2"] if W2 is not None else []):
+        _eq(getattr(m, n).grad, g[p + "d" + n])
+    with torch.no_grad():
+        _eq(m(A, X2, edges2), g[p + "out_fresh"])
+
+
+def test_wide_layer_and_layer_api(golden_models):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    Xw = torch.from_numpy(g["wide_X"])
+    m = oracle.OracleGCN2(At, Xw, edges, M, *(torch.from_numpy(g["wide_" + n]) for n in ("W1", "W2", "U")),
+                          apply_M_twice=True, nonlin2="relu")
+    out = m()
+    _eq(out, g["wide_out"])
+    out.backward(torch.from_numpy(g["wide_dOut"]))
+    for n in ("W1", "W2", "U"):
+        np.testing.assert_allclose(getattr(m, n).grad.numpy(), g["wide_d" + n], rtol=2e-5, atol=1e-5)
+    # the benchmarked layer == layer 2 of that model
+    with torch.no_grad():
+        Y1 = torch.relu(torch.matmul(m.AtXt, m.W1))
+    o2, dH, dW, dU = oracle.layer_fwd_bwd(At, Y1, M, m.W2.detach(), m.U.detach(), edges,
+                                          torch.from_numpy(g["wide_dOut"]))
+    _eq(o2, g["wide_out"])
+    np.testing.assert_allclose(dW.numpy(), g["wide_dW2"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(dU.numpy(), g["wide_dU"], rtol=2e-5, atol=1e-5)
+    assert dH.shape == Y1.shape
+
+
+def test_normalise_adjacency_small():
+    rng = np.random.default_rng(0)
+    T, N = 3, 12
+    dense = (rng.random((T, N, N)) < 0.2) * 1.0
+    for k in range(T):
+        np.fill_diagonal(dense[k], 0)
+    nz = np.nonzero(dense)
+    idx, val = oracle.normalise_adjacency(np.stack(nz), dense[nz], T, N)
+    ref = (dense + dense.transpose(0, 2, 1)) / 2 + np.eye(N)[None]
+    d = ref.sum(2)
+    ref = ref / np.sqrt(d)[:, :, None] / np.sqrt(d)[:, None, :]
+    got = np.zeros_like(ref)
+    got[idx[0], idx[1], idx[2]] = val
+    np.testing.assert_allclose(got, ref, rtol=1e-14)
+    key = (idx[0] * N + idx[1]) * N + idx[2]
+    assert np.all(np.diff(key) > 0)
