@@ -1,0 +1,151 @@
+/*
+ * tmgcn.h -- C ABI of libtmgcn_b200.so: the B200 (sm_100a) implementation of the
+ * TM-GCN propagation hot path.
+ *
+ * The reference (IBM/TM-GCN, TensorGCN-master/) has no FFI: its boundary is the
+ * Python call surface of func_MProduct / compute_AtXt / EmbeddingGCN*.  Each entry
+ * point below names the reference lines it replaces ("ref:"; ehf =
+ * embedding_help_functions.py).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     every call is asynchronous on it and re-entrant across streams;
+ *   - the library never allocates: outputs and workspaces are caller-owned,
+ *     workspace sizes are queried first (the *_plan / *_ws_bytes calls);
+ *   - return value 0 = ok, non-zero = error; tmgcn_last_error() gives the text
+ *     (thread-local).  No C++ exception crosses this boundary.
+ *
+ * Data layout ("CSR-of-slices"): a T x N x N sparse tensor is stored as ONE CSR
+ * over T*N rows: rowptr[T*N+1] int64 (row id = t*N + i), col[nnz] int32 (column
+ * inside the slice, ascending inside a row), val[nnz] fp32 (or fp64 where said).
+ * This is exactly the (t, i, j) order of a coalesced torch COO tensor
+ * (invariant 3).  Dense tensors are (T, N, F) fp32, time-major,
+ * contiguous -- the reference layout (ehf:204).
+ *
+ * M is banded lower-triangular (ref: SBM_our.py:88-96, read_data.py:56-62) and is
+ * passed as its band: band_w[t*b + i] = M[t, t-i], 0 <= i < b; a zero weight
+ * means "no entry" (the reference discovers the band with nonzero(M[:, j]),
+ * read_data.py:216).  With time sharding a rank owns T_out consecutive output
+ * slices and additionally holds `halo` (<= b-1) predecessor slices of every
+ * INPUT tensor in front of its own: input slice index = halo + t - i.
+ */
+#ifndef TMGCN_H
+#define TMGCN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMGCN_ABI_VERSION 1
+
+/* epilogue / nonlinearity selector (ref: ehf:284-289) */
+enum tmgcn_act { TMGCN_ACT_NONE = 0, TMGCN_ACT_RELU = 1, TMGCN_ACT_LEAKY = 2, TMGCN_ACT_SELU = 3 };
+
+const char *tmgcn_last_error(void);
+int tmgcn_abi_version(void);
+/* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
+int64_t tmgcn_launch_count(void);
+
+/* ---- helpers --------------------------------------------------------- */
+/* exclusive prefix sum of n int64 counts into out[n+1] (out[n] = total).
+ * ws: tmgcn_scan_ws_bytes(n) bytes. */
+size_t tmgcn_scan_ws_bytes(int64_t n);
+int tmgcn_exclusive_scan_i64(const int64_t *counts, int64_t *out, int64_t n, void *ws, void *stream);
+
+/* coalesced COO -> CSR-of-slices rowptr.  flat_row[nnz] int64 sorted ascending
+ * (t*N + i of every stored entry); writes rowptr[n_rows+1].
+ * Replaces the T boolean-mask passes of ref: ehf:561-572 / experiment_bitcoin_our.py:53-64. */
+int tmgcn_rowptr_from_sorted_rows(const int64_t *flat_row, int64_t nnz, int64_t n_rows, int64_t *rowptr,
+                                  void *stream);
+
+/* ---- (a) sparse M-transform  A~ = A x_3 M ------------------------------
+ * ref: func_MProduct, read_data.py:204-223 (bit-exact index output).
+ * plan: writes out_counts[T_out*N] = size of the union pattern of each output row.
+ * The caller scans them (tmgcn_exclusive_scan_i64) into out_rowptr and allocates
+ * col/val of out_rowptr[T_out*N] entries.  run: fills out_col / out_val.
+ * val_is_f64 selects fp64 (func_MProduct API parity) or fp32 values; sums are
+ * always accumulated in fp64 in ascending source-slice order. */
+int tmgcn_mtransform_sparse_plan(const int64_t *in_rowptr, const int32_t *in_col, int T_out, int halo, int64_t N,
+                                 const double *band_w, int b, int64_t *out_counts, void *stream);
+int tmgcn_mtransform_sparse_run(const int64_t *in_rowptr, const int32_t *in_col, const void *in_val, int T_out,
+                                int halo, int64_t N, const double *band_w, int b, const int64_t *out_rowptr,
+                                int32_t *out_col, void *out_val, int val_is_f64, void *stream);
+
+/* transpose every slice of a CSR-of-slices (for the backward SpMM).
+ * plan: counts[T*N] (zero-initialised by the call) = entries per transposed row.
+ * run: given the scanned t_rowptr, fills t_col / t_val with ascending columns.
+ * ws: nnz * 8 bytes + T*N*8 bytes (tmgcn_csr_transpose_ws_bytes). */
+size_t tmgcn_csr_transpose_ws_bytes(int64_t n_rows, int64_t nnz);
+int tmgcn_csr_transpose_plan(const int64_t *rowptr, const int32_t *col, int T, int64_t N, int64_t *counts,
+                             void *stream);
+int tmgcn_csr_transpose_run(const int64_t *rowptr, const int32_t *col, const float *val, int T, int64_t N,
+                            const int64_t *t_rowptr, int32_t *t_col, float *t_val, void *ws, void *stream);
+
+/* ---- (b) dense M-transform  X~ = X x_3 M  (time stencil) ------------------
+ * ref: ehf:204 / ehf:308 / ehf:346  (M @ X.reshape(T, N*F)).
+ * fwd: x_in (halo+T_out, NF) -> x_out (T_out, NF).
+ * bwd: g_out (T_out, NF) -> g_in (halo+T_out, NF) = M^T applied; the first `halo`
+ *      slices of g_in are the partial sums owed to the predecessor rank.
+ * band_w here is fp32 (device). NF = N*F. */
+int tmgcn_mtransform_dense_fwd(const float *x_in, float *x_out, int T_out, int halo, int64_t NF,
+                               const float *band_w, int b, void *stream);
+int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
+                               const float *band_w, int b, void *stream);
+
+/* ---- (d) facewise SpMM  P_t = A~_t . X_t -----------------------------------
+ * ref: the loop ehf:205-207 / ehf:309-311 and compute_AX ehf:301-305, 469-473.
+ * y[t, i, :] = act( sum_k val[k] * x[t, col[k], :] ), all T slices in one launch.
+ * The backward (dX_t = A~_t^T . dY_t) is the same call on the transposed CSR. */
+int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y, int T,
+                   int64_t N, int F, int act, void *stream);
+
+/* ---- (c) feature GEMM  Y = act(P . W) --------------------------------------
+ * ref: t.matmul(AtXt, W), ehf:222 / 330 / 344 / 486-489; nonlinearity ehf:332-335.
+ * p (R, K) . w (K, Nf) -> y (R, Nf), R = T*N rows; fp32 in/out.  K = Nf = 128 (and
+ * other multiples handled by the tensor-core path) run on tcgen05 with 3xTF32
+ * error compensation; anything else takes the SIMT fp32 kernel.
+ * bwd: given y (post-activation) and dy: dy <- dy * act'(y) implicitly, then
+ *   dp (R, K) = dy . w^T   and   dw (K, Nf) = p^T . dy  (slice-summed, deterministic).
+ * dw_ws: tmgcn_gemm_dw_ws_bytes(K, Nf) bytes of scratch for the per-CTA partials. */
+int tmgcn_gemm_xw_fwd(const float *p, const float *w, float *y, int64_t R, int K, int Nf, int act, void *stream);
+size_t tmgcn_gemm_dw_ws_bytes(int K, int Nf);
+int tmgcn_gemm_dw_dx_bwd(const float *p, const float *w, const float *y, const float *dy, float *dp, float *dw,
+                         int64_t R, int K, int Nf, int act, void *dw_ws, void *stream);
+
+/* ---- (e) edge-endpoint gather readout ------------------------------------
+ * ref: flat ids ehf:196-198; gather + concat ehf:228-230 / 351-353 / 491-493;
+ * classifier ehf:232 / 355 / 495.
+ * gather_fwd : z[e, :] = [ y[src[e], :] || y[dst[e], :] ]          (E, 2F)
+ * readout_fwd: out[e, :] = z[e, :] . u   without materialising z     (E, C), C <= 8
+ * src/dst are flat row ids t*N + node (int64). */
+int tmgcn_flat_edge_ids(const int64_t *edges /* (3,E) time,src,dst */, int64_t E, int64_t N, int64_t t_offset,
+                        int64_t *src, int64_t *dst, void *stream);
+int tmgcn_edge_gather_fwd(const float *y, const int64_t *src, const int64_t *dst, float *z, int64_t E, int F,
+                          void *stream);
+int tmgcn_edge_readout_fwd(const float *y, const int64_t *src, const int64_t *dst, const float *u, float *out,
+                           int64_t E, int F, int C, void *stream);
+/* backward.  The incidence plan makes the scatter-add deterministic: perm[2E] lists
+ * (e*2+half) grouped by touched row, row_ids[R_touched], seg_ptr[R_touched+1].
+ * gather_bwd : dy[row, :] = sum over incident (e, half) of dz[e, half*F:(half+1)*F]
+ * readout_bwd: dy[row, :] = sum dout[e, :] . u[half*F:(half+1)*F, :]^T ;  du = z^T . dout
+ * dy (n_rows, F) is fully written (rows no edge touches become 0). */
+int tmgcn_edge_gather_bwd(const float *dz, const int64_t *row_ids, const int64_t *seg_ptr, const int64_t *perm,
+                          int64_t n_touched, float *dy, int64_t n_rows, int F, void *stream);
+size_t tmgcn_edge_du_ws_bytes(int F, int C);
+int tmgcn_edge_readout_bwd(const float *y, const int64_t *src, const int64_t *dst, const float *u,
+                           const float *dout, const int64_t *row_ids, const int64_t *seg_ptr, const int64_t *perm,
+                           int64_t n_touched, float *dy, float *du, int64_t n_rows, int64_t E, int F, int C,
+                           void *du_ws, void *stream);
+
+/* ---- elementwise activation (layer boundary, ref: ehf:332-335) ----------- */
+int tmgcn_act_fwd(const float *x, float *y, int64_t n, int act, void *stream);
+int tmgcn_act_bwd(const float *y, const float *dy, float *dx, int64_t n, int act, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMGCN_H */

@@ -1,0 +1,472 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden
+fixtures.  Bars: sparse indices bit-exact; embeddings / logits
+||d||_inf / ||ref||_inf <= 1e-5; gradients <= 1e-4; identical argmax wherever the
+top-2 logit margin exceeds 1e-4 * ||out||_inf."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import MPRODUCT_CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL_OUT = 1e-5
+TOL_GRAD = 1e-4
+
+
+@pytest.fixture(scope="module")
+def tg():
+    import tmgcn_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    tmgcn_b200._lib.load(build_if_missing=False)   # the shipped .so must be there: no fallback
+    return tmgcn_b200
+
+
+def relerr(got, ref):
+    got = got.detach().double().cpu() if torch.is_tensor(got) else torch.as_tensor(got).double()
+    ref = ref.detach().double().cpu() if torch.is_tensor(ref) else torch.as_tensor(ref).double()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    denom = ref.abs().max().item()
+    return (got - ref).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def assert_same_argmax(got, ref):
+    got, ref = got.detach().cpu().double(), torch.as_tensor(ref).double()
+    top2 = torch.topk(ref, 2, dim=1).values
+    sure = (top2[:, 0] - top2[:, 1]) > 1e-4 * ref.abs().max()
+    assert torch.equal(got.argmax(1)[sure], ref.argmax(1)[sure])
+
+
+# --------------------------------------------------------------------------
+# integer plumbing
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 5, 4096, 4097, 1_000_003])
+def test_exclusive_scan(tg, n):
+    from tmgcn_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    c = torch.randint(0, 50, (n,), generator=g, dtype=torch.int64)
+    out = ops.exclusive_scan(c.cuda()).cpu()
+    ref = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(c, 0)])
+    assert torch.equal(out, ref)
+
+
+def test_csr_from_coo_ragged(tg):
+    # empty first/last slices, empty rows, a row with many entries
+    T, N = 5, 7
+    idx = torch.tensor([[1, 1, 1, 3, 3], [0, 6, 6, 2, 2], [3, 0, 5, 1, 2]])
+    val = torch.arange(5, dtype=torch.float64)
+    csr = tg.SliceCSR.from_coo(idx, val, T, N)
+    rp = csr.rowptr.cpu()
+    assert rp[0] == 0 and rp[-1] == 5 and rp.numel() == T * N + 1
+    counts = (rp[1:] - rp[:-1])
+    assert counts[1 * N + 0] == 1 and counts[1 * N + 6] == 2 and counts[3 * N + 2] == 2 and counts.sum() == 5
+    idx2, val2 = csr.to_coo()
+    assert torch.equal(idx2.cpu(), idx) and torch.equal(val2.cpu().double(), val)
+    empty = tg.SliceCSR.from_coo(torch.zeros(3, 0, dtype=torch.int64), torch.zeros(0), 2, 3)
+    assert empty.nnz == 0 and torch.equal(empty.rowptr.cpu(), torch.zeros(7, dtype=torch.int64))
+
+
+# --------------------------------------------------------------------------
+# (a) sparse M-transform: bit-exact indices
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name", MPRODUCT_CASES)
+def test_func_mproduct_golden(tg, golden_mproduct, name):
+    g = golden_mproduct
+    T, N, _ = (int(x) for x in g[name + "_shape"])
+    C = torch.sparse_coo_tensor(torch.from_numpy(g[name + "_in_idx"]), torch.from_numpy(g[name + "_in_val"]),
+                                (T, N, N)).coalesce()
+    out = tg.func_MProduct(C, torch.from_numpy(g[name + "_M"]), no_diag=int(g[name + "_b"]))
+    assert out.is_coalesced() and out.dtype == torch.float64
+    assert out._indices().dtype == torch.int64
+    assert torch.equal(out._indices().cpu(), torch.from_numpy(g[name + "_out_idx"]))
+    np.testing.assert_allclose(out._values().cpu().numpy(), g[name + "_out_val"], rtol=1e-13, atol=0)
+
+
+def test_func_mproduct_chess(tg, golden_chess):
+    g = golden_chess
+    T, N, _ = (int(x) for x in g["shape"])
+    C = torch.sparse_coo_tensor(torch.from_numpy(g["in_idx"].astype(np.int64)), torch.from_numpy(g["in_val"]),
+                                (T, N, N)).coalesce()
+    out = tg.func_MProduct(C, torch.from_numpy(g["M"]))
+    assert torch.equal(out._indices().cpu(), torch.from_numpy(g["out_idx"].astype(np.int64)))
+    np.testing.assert_allclose(out._values().cpu().numpy(), g["out_val"], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("T,N,m,rho,b,norm", [(20, 3000, 9000, 0.9, 10, False), (9, 500, 4000, 0.0, 20, True),
+                                               (6, 64, 2000, 0.5, 3, False), (33, 200, 300, 0.7, 32, False)])
+def test_mtransform_sparse_vs_oracle(tg, T, N, m, rho, b, norm):
+    from tmgcn_b200 import ops, synth
+    idx, val = synth.synth_coo(N, T, m, rho, seed=T * 1000 + b)
+    M = oracle.create_matrix_M(T, b, normalize=norm)
+    ref_idx, ref_val = oracle.func_MProduct(idx.numpy(), val.numpy(), (T, N, N), M.numpy(), no_diag=b)
+    band = tg.Band(M)
+    # fp64 values (API parity) and fp32 values (pipeline layout)
+    for dt, tol in ((torch.float64, 1e-13), (torch.float32, 2e-7)):
+        csr = tg.SliceCSR.from_coo(idx, val, T, N, dtype=dt)
+        out = ops.mtransform_sparse(csr, band)
+        oi, ov = out.to_coo()
+        assert torch.equal(oi.cpu(), torch.from_numpy(ref_idx))
+        np.testing.assert_allclose(ov.cpu().double().numpy(), ref_val, rtol=tol, atol=0)
+    # time-sharded: two ranks, halo = b-1 input slices from the predecessor
+    cut = T // 2
+    halo = min(b - 1, cut)
+    sel_lo = idx[0] < cut
+    sel_hi = idx[0] >= cut - halo
+    lo = tg.SliceCSR.from_coo(idx[:, sel_lo], val[sel_lo], cut, N)
+    idx_hi = idx[:, sel_hi].clone()
+    idx_hi[0] -= cut - halo
+    hi = tg.SliceCSR.from_coo(idx_hi, val[sel_hi], T - cut + halo, N)
+    o_lo = ops.mtransform_sparse(lo, band, 0, cut, 0)
+    o_hi = ops.mtransform_sparse(hi, band, cut, T, halo)
+    i_lo, v_lo = o_lo.to_coo()
+    i_hi, v_hi = o_hi.to_coo()
+    i_hi = i_hi.clone()
+    i_hi[0] += cut
+    assert torch.equal(torch.cat([i_lo, i_hi], 1).cpu(), torch.from_numpy(ref_idx))
+    np.testing.assert_allclose(torch.cat([v_lo, v_hi]).cpu().double().numpy(), ref_val, rtol=2e-7, atol=0)
+
+
+def test_mtransform_sparse_zero_weight_and_cancellation(tg):
+    """explicit zeros inside the band drop the source slice (nonzero(M[:, j]), ref: read_data.py:216);
+    sums that cancel to 0.0 stay stored (coalesce never prunes)."""
+    from tmgcn_b200 import ops
+    T, N = 4, 5
+    M = oracle.create_matrix_M(T, 3)
+    M[2, 1] = 0.0
+    M[3, 2] = -1.0
+    idx = torch.tensor([[0, 1, 2, 2, 3], [0, 1, 1, 4, 1], [1, 2, 3, 4, 3]])
+    val = torch.tensor([1.0, 2.0, 3.0, 4.0, 3.0], dtype=torch.float64)
+    ref_idx, ref_val = oracle.func_MProduct(idx.numpy(), val.numpy(), (T, N, N), M.numpy())
+    out = ops.mtransform_sparse(tg.SliceCSR.from_coo(idx, val, T, N, dtype=torch.float64), tg.Band(M))
+    oi, ov = out.to_coo()
+    assert torch.equal(oi.cpu(), torch.from_numpy(ref_idx))
+    np.testing.assert_allclose(ov.cpu().numpy(), ref_val, rtol=1e-14, atol=0)
+    assert (ref_val == 0).any()      # the (3,1,3) entry: 1*3 + (-1)*3
+
+
+def test_csr_transpose(tg):
+    from tmgcn_b200 import synth
+    T, N = 5, 400
+    idx, val = synth.synth_coo(N, T, 3000, 0.5, seed=7)
+    # make it unsymmetric and add a hub column (long transposed row)
+    keep = torch.rand(idx.shape[1], generator=torch.Generator().manual_seed(1)) < 0.7
+    idx, val = idx[:, keep], val[keep]
+    hub = torch.stack([torch.full((N,), 2), torch.arange(N), torch.full((N,), 17)])
+    idx = torch.cat([idx, hub], 1)
+    val = torch.cat([val, torch.rand(N, dtype=torch.float64)])
+    C = torch.sparse_coo_tensor(idx, val, (T, N, N)).coalesce()
+    csr = tg.SliceCSR.from_coo(C._indices(), C._values(), T, N)
+    tr = csr.transpose()
+    ti, tv = tr.to_coo()
+    Ct = C.transpose(1, 2).coalesce()
+    assert torch.equal(ti.cpu(), Ct._indices())
+    assert torch.equal(tv.cpu(), Ct._values().float())
+
+
+# --------------------------------------------------------------------------
+# (b) dense M-transform
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("T,b,NF", [(12, 1, 64), (12, 2, 96), (7, 3, 10), (30, 5, 1028), (25, 10, 4096),
+                                    (40, 20, 260), (5, 20, 128), (70, 32, 36), (34, 20, 2001)])
+@pytest.mark.parametrize("norm", [False, True])
+def test_stencil_fwd_bwd(tg, T, b, NF, norm):
+    from tmgcn_b200 import ops
+    g = torch.Generator().manual_seed(T * 100 + b)
+    M = oracle.create_matrix_M(T, b, normalize=norm)
+    band = tg.Band(M)
+    X = torch.rand(T, NF, 1, generator=g)
+    G = torch.randn(T, NF, 1, generator=g)
+    ref = (M @ X.double().reshape(T, -1)).reshape(X.shape)
+    ref_g = (M.T @ G.double().reshape(T, -1)).reshape(X.shape)
+    out = ops.stencil_fwd(X.cuda(), band)
+    assert relerr(out, ref) <= 2e-6
+    gin = ops.stencil_bwd(G.cuda(), band)
+    assert relerr(gin, ref_g) <= 2e-6
+    # sharded with halo: rank 1 owns [cut, T)
+    cut = T // 2
+    halo = min(band.b - 1, cut)
+    out_hi = ops.stencil_fwd(X[cut - halo:].cuda().contiguous(), band, cut, T, halo)
+    assert relerr(out_hi, ref[cut:]) <= 2e-6
+    out_lo = ops.stencil_fwd(X[:cut].cuda().contiguous(), band, 0, cut, 0)
+    assert relerr(out_lo, ref[:cut]) <= 2e-6
+    g_hi = ops.stencil_bwd(G[cut:].cuda().contiguous(), band, cut, T, halo)      # (halo + T-cut) slices
+    g_lo = ops.stencil_bwd(G[:cut].cuda().contiguous(), band, 0, cut, 0)
+    total = torch.zeros(T, NF, 1, dtype=torch.float64)
+    total[:cut] += g_lo.double().cpu()
+    total[cut - halo:] += g_hi.double().cpu()        # halo part = what rank 1 owes rank 0
+    assert relerr(total, ref_g) <= 2e-6
+
+
+# --------------------------------------------------------------------------
+# (d) SpMM
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("F", [1, 2, 3, 6, 8, 20, 32, 100, 128, 256])
+def test_spmm_vs_oracle(tg, F):
+    from tmgcn_b200 import ops, synth
+    T, N = 4, 700
+    idx, val = synth.synth_coo(N, T, 5000, 0.6, seed=F)
+    # hub rows: one with 40 entries, one dense row (> 32, multiple chunks)
+    hub = torch.stack([torch.full((N,), 1), torch.full((N,), 5), torch.arange(N)])
+    idx = torch.cat([idx, hub], 1)
+    val = torch.cat([val, torch.rand(N, dtype=torch.float64)])
+    C = torch.sparse_coo_tensor(idx, val, (T, N, N)).coalesce()
+    A = oracle.split_slices(C._indices().numpy(), C._values().numpy(), T, N)
+    X = torch.rand(T, N, F, generator=torch.Generator().manual_seed(F), dtype=torch.float64)
+    ref = oracle.compute_AX(A, X)
+    csr = tg.SliceCSR.from_coo(C._indices(), C._values(), T, N)
+    out = ops.spmm_raw(csr, X.float().cuda())
+    assert relerr(out, ref) <= TOL_OUT
+    # transposed (backward) product
+    ref_t = oracle.compute_AX([a.t().coalesce() for a in A], X)
+    out_t = ops.spmm_raw(csr.transpose(), X.float().cuda())
+    assert relerr(out_t, ref_t) <= TOL_OUT
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky", "selu"])
+def test_spmm_activation_and_grad(tg, act):
+    from tmgcn_b200 import ops, synth
+    T, N, F = 3, 300, 12
+    idx, val = synth.synth_coo(N, T, 2000, 0.5, seed=3)
+    A = oracle.split_slices(idx.numpy(), val.numpy(), T, N)
+    csr = tg.SliceCSR.from_coo(idx, val, T, N)
+    g = torch.Generator().manual_seed(5)
+    X = (torch.rand(T, N, F, generator=g, dtype=torch.float64) - 0.5)
+    G = torch.randn(T, N, F, generator=g)
+    Xr = X.clone().requires_grad_(True)
+    ref = oracle.nonlin(act)(torch.stack([torch.sparse.mm(A[k], Xr[k]) for k in range(T)]))
+    ref.backward(G.double())
+    Xd = X.float().cuda().requires_grad_(True)
+    out = ops.spmm(csr, Xd, act)
+    out.backward(G.cuda())
+    assert relerr(out, ref) <= TOL_OUT
+    assert relerr(Xd.grad, Xr.grad) <= TOL_GRAD
+
+
+# --------------------------------------------------------------------------
+# (c) GEMM
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("R,K,Nf", [(1000, 2, 6), (777, 6, 6), (500, 6, 2), (300, 32, 48), (2000, 128, 128),
+                                    (130, 128, 128), (4100, 128, 64), (257, 100, 36), (640, 256, 128)])
+@pytest.mark.parametrize("act", ["none", "relu", "leaky", "selu"])
+def test_gemm_fwd_bwd(tg, R, K, Nf, act):
+    from tmgcn_b200 import ops
+    g = torch.Generator().manual_seed(R + K)
+    P = torch.randn(R, K, generator=g)
+    W = torch.randn(K, Nf, generator=g) / K ** 0.5
+    G = torch.randn(R, Nf, generator=g)
+    Pr, Wr = P.double().requires_grad_(True), W.double().requires_grad_(True)
+    ref = oracle.nonlin(act)(Pr @ Wr)
+    ref.backward(G.double())
+    Pd, Wd = P.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    out = ops.gemm_xw(Pd, Wd, act)
+    out.backward(G.cuda())
+    assert relerr(out, ref) <= TOL_OUT
+    assert relerr(Pd.grad, Pr.grad) <= TOL_GRAD
+    assert relerr(Wd.grad, Wr.grad) <= TOL_GRAD
+
+
+# --------------------------------------------------------------------------
+# (e) edge readout
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("F,Cc", [(2, 2), (6, 3), (16, 1), (128, 2), (100, 8)])
+def test_edge_readout_and_gather(tg, F, Cc):
+    from tmgcn_b200 import ops
+    T, N, E = 5, 60, 700
+    g = torch.Generator().manual_seed(F)
+    Y = torch.randn(T, N, F, generator=g)
+    U = torch.randn(2 * F, Cc, generator=g)
+    edges = torch.stack([torch.randint(0, T, (E,), generator=g), torch.randint(0, N, (E,), generator=g),
+                         torch.randint(0, N, (E,), generator=g)])
+    edges[:, :40] = edges[:, :1]          # heavy duplicates: the scatter-add must accumulate them
+    dOut = torch.randn(E, Cc, generator=g)
+    dZ = torch.randn(E, 2 * F, generator=g)
+    src, trg = oracle.flat_edge_ids(edges, N)
+    Yr, Ur = Y.double().requires_grad_(True), U.double().requires_grad_(True)
+    Zr = torch.cat((Yr.reshape(-1, F)[src], Yr.reshape(-1, F)[trg]), 1)
+    ref = Zr @ Ur
+    ref.backward(dOut.double())
+    plan = tg.EdgePlan(edges, N)
+    assert torch.equal(plan.src.cpu(), src) and torch.equal(plan.dst.cpu(), trg)
+    Yd, Ud = Y.cuda().requires_grad_(True), U.cuda().requires_grad_(True)
+    out = ops.edge_readout(Yd, Ud, plan)
+    out.backward(dOut.cuda())
+    assert relerr(out, ref) <= TOL_OUT
+    assert relerr(Yd.grad, Yr.grad) <= TOL_GRAD
+    assert relerr(Ud.grad, Ur.grad) <= TOL_GRAD
+    # plain gather (E, 2F) and its scatter-add backward
+    Yr2 = Y.double().requires_grad_(True)
+    Zr2 = torch.cat((Yr2.reshape(-1, F)[src], Yr2.reshape(-1, F)[trg]), 1)
+    Zr2.backward(dZ.double())
+    Yd2 = Y.cuda().requires_grad_(True)
+    Z = ops.edge_gather(Yd2, plan)
+    Z.backward(dZ.cuda())
+    assert torch.equal(Z.cpu(), Zr2.detach().float())       # pure data movement: exact
+    assert relerr(Yd2.grad, Yr2.grad) <= TOL_GRAD
+    # determinism of the scatter-add
+    Yd3 = Y.cuda().requires_grad_(True)
+    ops.edge_gather(Yd3, plan).backward(dZ.cuda())
+    assert torch.equal(Yd3.grad, Yd2.grad)
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "leaky", "selu"])
+def test_activation(tg, act):
+    from tmgcn_b200 import ops
+    x = torch.randn(10_001, generator=torch.Generator().manual_seed(1))
+    xr = x.double().requires_grad_(True)
+    ref = oracle.nonlin(act)(xr)
+    ref.backward(torch.ones_like(ref))
+    xd = x.cuda().requires_grad_(True)
+    out = ops.activation(xd, act)
+    out.backward(torch.ones_like(out))
+    assert relerr(out, ref) <= 1e-6 and relerr(xd.grad, xr.grad) <= 1e-6
+
+
+# --------------------------------------------------------------------------
+# modules against the reference's own outputs (golden) and the oracle
+# --------------------------------------------------------------------------
+def _inputs(g):
+    T, N = (int(x) for x in g["TN"])
+    M = torch.from_numpy(g["M"])
+    At = oracle.split_slices(g["Ct_idx"], g["Ct_val"], T, N)
+    A = oracle.split_slices(g["C_idx"], g["C_val"], T, N)
+    X, X2 = torch.from_numpy(g["X"]), torch.from_numpy(g["X2"])
+    edges, edges2 = torch.from_numpy(g["edges"]), torch.from_numpy(g["edges2"])
+    return T, N, M, At, A, X, X2, edges, edges2
+
+
+def _load(mod, g, prefix, names):
+    with torch.no_grad():
+        for n in names:
+            getattr(mod, n).copy_(torch.from_numpy(g[prefix + n]))
+
+
+def test_module_gcn1_golden(tg, golden_models):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    m = tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=True, use_Minv=False)
+    _load(m, g, "gcn1_", ["W", "U"])
+    assert relerr(m.AtXt, g["gcn1_AtXt"]) <= TOL_OUT
+    out = m()
+    assert relerr(out, g["gcn1_out"]) <= TOL_OUT
+    assert_same_argmax(out, g["gcn1_out"])
+    out.backward(torch.from_numpy(g["gcn1_dOut"]).cuda())
+    assert relerr(m.W.grad, g["gcn1_dW"]) <= TOL_GRAD
+    assert relerr(m.U.grad, g["gcn1_dU"]) <= TOL_GRAD
+    with torch.no_grad():
+        fresh = m(At, X2, edges2)
+        assert relerr(fresh, g["gcn1_out_fresh"]) <= TOL_OUT
+        # cached == recomputed, bit for bit (SURVEY section 4 invariant 2)
+        assert torch.equal(m(At, X, edges), m())
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("relu", dict(nonlin2="relu")), ("leaky", dict(nonlin2="leaky")), ("selu", dict(nonlin2="selu")),
+    ("selu_m2", dict(nonlin2="selu", apply_M_twice=True)),
+    ("relu_m3", dict(nonlin2="relu", apply_M_twice=True, apply_M_three_times=True))])
+def test_module_gcn2_golden(tg, golden_models, tag, kw):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    p = "gcn2_" + tag + "_"
+    m = tg.EmbeddingGCN2(At, X, edges, M, hidden_feat=[6, 6, 2], condensed_W=True, use_Minv=False, **kw)
+    _load(m, g, p, ["W1", "W2", "U"])
+    out = m()
+    assert relerr(out, g[p + "out"]) <= TOL_OUT
+    assert_same_argmax(out, g[p + "out"])
+    out.backward(torch.from_numpy(g["gcn1_dOut"]).cuda())
+    for n in ("W1", "W2", "U"):
+        assert relerr(getattr(m, n).grad, g[p + "d" + n]) <= TOL_GRAD, n
+    with torch.no_grad():
+        assert relerr(m(At, X2, edges2), g[p + "out_fresh"]) <= TOL_OUT
+
+
+@pytest.mark.parametrize("tag,hf", [("kw1", [6, 2]), ("kw2", [6, 6, 2])])
+def test_module_kwgcn_golden(tg, golden_models, tag, hf):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    p = tag + "_"
+    m = tg.EmbeddingKWGCN(A, X, edges, hidden_feat=hf, nonlin2="leaky")
+    names = ["W1", "U"] + (["W2"] if len(hf) == 3 else [])
+    _load(m, g, p, names)
+    out = m()
+    assert relerr(out, g[p + "out"]) <= TOL_OUT
+    out.backward(torch.from_numpy(g["gcn1_dOut"]).cuda())
+    for n in names:
+        assert relerr(getattr(m, n).grad, g[p + "d" + n]) <= TOL_GRAD, n
+    with torch.no_grad():
+        assert relerr(m(A, X2, edges2), g[p + "out_fresh"]) <= TOL_OUT
+
+
+def test_module_wide_golden(tg, golden_models):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    m = tg.EmbeddingGCN2(At, torch.from_numpy(g["wide_X"]), edges, M, hidden_feat=[48, 16, 3], condensed_W=True,
+                         use_Minv=False, apply_M_twice=True, nonlin2="relu")
+    _load(m, g, "wide_", ["W1", "W2", "U"])
+    out = m()
+    assert relerr(out, g["wide_out"]) <= TOL_OUT
+    out.backward(torch.from_numpy(g["wide_dOut"]).cuda())
+    for n in ("W1", "W2", "U"):
+        assert relerr(getattr(m, n).grad, g["wide_d" + n]) <= TOL_GRAD, n
+
+
+def test_module_seed_reproduces_reference_init(tg, golden_models):
+    """same torch seed => same randn draws in the reference's order (ehf:188-192)."""
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    torch.manual_seed(100)
+    m = tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=True, use_Minv=False)
+    assert torch.equal(m.W.detach().cpu(), torch.from_numpy(g["gcn1_W"]))
+    assert torch.equal(m.U.detach().cpu(), torch.from_numpy(g["gcn1_U"]))
+    torch.manual_seed(300)
+    k = tg.EmbeddingKWGCN(A, X, edges, hidden_feat=[6, 6, 2], nonlin2="leaky")
+    assert torch.equal(k.W2.detach().cpu(), torch.from_numpy(g["kw2_W2"]))
+    assert torch.equal(k.W1.detach().cpu(), torch.from_numpy(g["kw2_W1"]))
+
+
+def test_module_errors(tg, golden_models):
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    with pytest.raises(NotImplementedError):
+        tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=True, use_Minv=True)
+    with pytest.raises(NotImplementedError):
+        tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=False, use_Minv=False)
+    with pytest.raises(AssertionError):
+        tg.func_MProduct(torch.eye(3).reshape(1, 3, 3).to_sparse(), torch.eye(2, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        tg.Band(torch.ones(4, 4))
+    with pytest.raises(RuntimeError):
+        from tmgcn_b200 import ops
+        ops.stencil_fwd(torch.zeros(4, 8, 1).cuda(), tg.Band(oracle.create_matrix_M(4, 3)), 0, 4, 3)  # halo > b-1
+
+
+# --------------------------------------------------------------------------
+# the benchmarked layer at a mid size, F = 128 (tensor-core GEMM path)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("act", ["none", "relu"])
+def test_layer_f128_vs_oracle(tg, act):
+    from tmgcn_b200 import ops, synth
+    T, N, F, Cc, b = 12, 2000, 128, 2, 10
+    idx, val = synth.synth_coo(N, T, 8000, 0.9, seed=99)
+    M = oracle.create_matrix_M(T, b)
+    band = tg.Band(M)
+    ref_idx, ref_val = oracle.func_MProduct(idx.numpy(), val.numpy(), (T, N, N), M.numpy())
+    At_ref = oracle.split_slices(ref_idx, ref_val, T, N)
+    At = ops.mtransform_sparse(tg.SliceCSR.from_coo(idx, val, T, N), band)
+    g = torch.Generator().manual_seed(1)
+    H = torch.rand(T, N, F, generator=g)
+    W = torch.randn(F, F, generator=g) / F ** 0.5
+    U = torch.randn(2 * F, Cc, generator=g)
+    E = 5000
+    edges = synth.synth_edges(At, E).cpu()
+    dOut = torch.randn(E, Cc, generator=g)
+    out_r, dH_r, dW_r, dU_r = oracle.layer_fwd_bwd(At_ref, H, M, W, U, edges, dOut, act, as_reference=False)
+    layer = tg.TMGCNLayer(At, band, tg.EdgePlan(edges, N), W, U, act)
+    Hd = H.cuda().requires_grad_(True)
+    out = layer(Hd)
+    out.backward(dOut.cuda())
+    assert relerr(out, out_r) <= TOL_OUT
+    assert_same_argmax(out, out_r)
+    assert relerr(Hd.grad, dH_r) <= TOL_GRAD
+    assert relerr(layer.W.grad, dW_r) <= TOL_GRAD
+    assert relerr(layer.U.grad, dU_r) <= TOL_GRAD

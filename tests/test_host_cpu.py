@@ -1,0 +1,115 @@
+"""CPU-side checks: the C ABI library loads and exports every symbol the header
+declares, and the host logic (band extraction, M construction, input generator)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "tmgcn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tmgcn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import tmgcn_b200
+    from tmgcn_b200 import _lib
+    lib = _lib.load()                      # builds with nvcc if the .so is absent
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/tmgcn.h but not exported"
+        assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype"
+    assert sorted(_lib.PROTOTYPES) == syms
+    assert lib.tmgcn_abi_version() == 1
+    assert isinstance(lib.tmgcn_last_error(), bytes)
+    # size queries are host-only and safe without a GPU
+    assert lib.tmgcn_scan_ws_bytes(10_000) >= 8
+    assert lib.tmgcn_csr_transpose_ws_bytes(10, 100) == 100 * 8 + 10 * 8
+
+
+def test_product_fails_loudly_without_gpu():
+    import tmgcn_b200
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tmgcn_b200.func_MProduct(torch.eye(3).reshape(1, 3, 3).to_sparse(), torch.eye(1, dtype=torch.float64))
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = "import sys; sys.path.insert(0, %r); import tmgcn_b200; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout.strip()
+    assert out == "False"
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tmgcn_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read(), f"{f} mentions the oracle"
+
+
+@pytest.mark.parametrize("T,b,norm", [(8, 3, False), (8, 3, True), (12, 20, False), (5, 1, False), (95, 20, True)])
+def test_create_matrix_M_and_band(T, b, norm):
+    import tmgcn_b200
+    M = tmgcn_b200.create_matrix_M(T, b, normalize=norm)
+    ref = oracle.create_matrix_M(T, b, normalize=norm)
+    np.testing.assert_allclose(M.numpy(), ref.numpy(), rtol=1e-15, atol=0)
+    band = tmgcn_b200.Band(M)
+    assert band.b == min(b, T) and band.T == T
+    rebuilt = torch.zeros(T, T, dtype=torch.float64)
+    for t in range(T):
+        for i in range(band.b):
+            if t - i >= 0:
+                rebuilt[t, t - i] = band.w[t, i]
+    assert torch.equal(rebuilt, M)
+    # weights that would reach before t=0 are zero
+    for t in range(min(band.b - 1, T)):
+        assert torch.all(band.w[t, t + 1:] == 0)
+
+
+def test_band_rejects_non_banded():
+    import tmgcn_b200
+    with pytest.raises(NotImplementedError):
+        tmgcn_b200.Band(torch.ones(5, 5, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        tmgcn_b200.Band(torch.tril(torch.ones(40, 40, dtype=torch.float64)))   # band 40 > 32
+    with pytest.raises(ValueError):
+        tmgcn_b200.Band(torch.ones(3, 4))
+
+
+def test_synth_generator_matches_reference_preparation():
+    from tmgcn_b200 import synth
+    N, T, m = 40, 5, 120
+    idx, val = synth.synth_coo(N, T, m, 0.8, seed=3)
+    key = (idx[0] * N + idx[1]) * N + idx[2]
+    assert torch.all(key[1:] > key[:-1])                      # coalesced (t, i, j) order
+    dense = torch.zeros(T, N, N, dtype=torch.float64)
+    dense[idx[0], idx[1], idx[2]] = val
+    assert torch.allclose(dense, dense.transpose(1, 2), rtol=1e-15)
+    # undo the normalisation: every slice has a full diagonal and row sums consistent with D^-1/2 (A+I) D^-1/2
+    for t in range(T):
+        assert torch.all(torch.diagonal(dense[t]) > 0)
+    # the same raw pattern pushed through the oracle's restatement of read_data.py gives the same tensor
+    raw = dense.clone()
+    struct = (raw != 0)
+    for t in range(T):
+        struct[t].fill_diagonal_(False)
+    # raw graph: unknown direction multiplicities, so compare the normalisation on the symmetric 0/0.5/1 pattern
+    # recovered from value ratios is not possible in general; instead check D^-1/2 scaling directly
+    for t in range(T):
+        d = 1.0 / torch.diagonal(dense[t])                    # (A+I)_ii = 1 => value = 1/deg_i
+        Aplus = dense[t] * torch.sqrt(d)[:, None] * torch.sqrt(d)[None, :]
+        assert torch.allclose(Aplus.sum(1), d, rtol=1e-12)    # row sums of A+I equal the degrees
+        off = Aplus[struct[t]]
+        assert torch.all((torch.abs(off - 0.5) < 1e-12) | (torch.abs(off - 1.0) < 1e-12))
+    # temporal persistence: consecutive slices share most of their pattern at rho = 0.8
+    shared = (struct[1:] & struct[:-1]).sum().item() / struct[1:].sum().item()
+    assert shared > 0.55

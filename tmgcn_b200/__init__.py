@@ -1,0 +1,15 @@
+"""tmgcn_b200 -- B200 (sm_100a) implementation of the TM-GCN propagation hot path.
+
+Host-side mirror of the reference's call surface (`func_MProduct`,
+`create_matrix_M`, `EmbeddingGCN`, `EmbeddingGCN2`, `EmbeddingKWGCN`) over the
+C ABI of libtmgcn_b200.so (include/tmgcn.h).  Importing the package does not
+need a GPU; calling anything on the hot path does, and fails loudly without one.
+"""
+from . import _lib  # noqa: F401
+from .modules import (EmbeddingGCN, EmbeddingGCN2, EmbeddingKWGCN, TMGCNLayer, create_matrix_M, func_MProduct,
+                      split_slices)
+from .ops import Band, EdgePlan, SliceCSR
+
+__all__ = ["EmbeddingGCN", "EmbeddingGCN2", "EmbeddingKWGCN", "TMGCNLayer", "create_matrix_M", "func_MProduct",
+           "split_slices", "Band", "EdgePlan", "SliceCSR"]
+__version__ = "0.1.0"

@@ -1,0 +1,71 @@
+// (c) feature GEMM entry points: dispatch between the tcgen05 3xTF32 kernel
+// (gemm_tc.cu) and the SIMT fp32 kernel (gemm_simt.cu).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace tmgcn {
+int dw_max_chunks();
+int gemm_simt_fwd(const float *p, const float *w, float *y, int64_t R, int K, int Nf, int act, cudaStream_t st);
+int gemm_simt_dp(const float *w, const float *y, const float *dy, float *dp, int64_t R, int K, int Nf, int act,
+                 cudaStream_t st);
+int gemm_simt_dw(const float *p, const float *y, const float *dy, float *dw, int64_t R, int K, int Nf, int act,
+                 float *ws, cudaStream_t st);
+
+// tensor-core path (gemm_tc.cu)
+bool gemm_tc_eligible(int64_t R, int K, int Nf);
+int gemm_tc_fwd(const float *a, const float *w, float *c, int64_t R, int K, int Nf, int act, bool trans_w,
+                const float *yaux, cudaStream_t st);
+
+static bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TMGCN_DISABLE_TC");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+}  // namespace tmgcn
+
+using namespace tmgcn;
+
+extern "C" {
+
+int tmgcn_gemm_xw_fwd(const float *p, const float *w, float *y, int64_t R, int K, int Nf, int act, void *stream) {
+    TMGCN_REQUIRE(R >= 0 && K >= 1 && Nf >= 1, "gemm_xw_fwd: bad sizes R=%lld K=%d Nf=%d", (long long)R, K, Nf);
+    TMGCN_REQUIRE(act >= 0 && act <= 3, "gemm_xw_fwd: unknown activation %d", act);
+    if (R == 0) return 0;
+    TMGCN_REQUIRE(p && w && y, "gemm_xw_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tc_enabled() && gemm_tc_eligible(R, K, Nf)) return gemm_tc_fwd(p, w, y, R, K, Nf, act, false, nullptr, st);
+    return gemm_simt_fwd(p, w, y, R, K, Nf, act, st);
+}
+
+size_t tmgcn_gemm_dw_ws_bytes(int K, int Nf) { return (size_t)dw_max_chunks() * (size_t)K * (size_t)Nf * sizeof(float); }
+
+int tmgcn_gemm_dw_dx_bwd(const float *p, const float *w, const float *y, const float *dy, float *dp, float *dw,
+                         int64_t R, int K, int Nf, int act, void *dw_ws, void *stream) {
+    TMGCN_REQUIRE(R >= 0 && K >= 1 && Nf >= 1, "gemm_bwd: bad sizes R=%lld K=%d Nf=%d", (long long)R, K, Nf);
+    TMGCN_REQUIRE(act >= 0 && act <= 3, "gemm_bwd: unknown activation %d", act);
+    TMGCN_REQUIRE(act == TMGCN_ACT_NONE || y, "gemm_bwd: y is required when an activation is fused");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (R == 0) {
+        if (dw) TMGCN_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * Nf * sizeof(float), st));
+        return 0;
+    }
+    TMGCN_REQUIRE(w && dy, "gemm_bwd: null pointer");
+    if (dp) {
+        int rc;
+        if (tc_enabled() && gemm_tc_eligible(R, Nf, K))
+            rc = gemm_tc_fwd(dy, w, dp, R, Nf, K, act, true, act == TMGCN_ACT_NONE ? nullptr : y, st);
+        else
+            rc = gemm_simt_dp(w, y, dy, dp, R, K, Nf, act, st);
+        if (rc) return rc;
+    }
+    if (dw) {
+        TMGCN_REQUIRE(p && dw_ws, "gemm_bwd: p and dw_ws are required for dW");
+        if (gemm_simt_dw(p, y, dy, dw, R, K, Nf, act, (float *)dw_ws, st)) return 1;
+    }
+    return 0;
+}
+}

@@ -1,0 +1,370 @@
+// (a) sparse M-transform: per-row sorted merge of the band's CSR rows, plus the
+// integer plumbing around it (exclusive scan, COO->CSR row pointers, per-slice
+// CSR transpose for the backward SpMM).  All of it is HBM/latency-bound integer
+// work: coalesced where the data allows, grids sized in multiples of the SM count.
+//
+// ref: func_MProduct, TensorGCN-master/read_data.py:204-223.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace tmgcn {
+
+// ------------------------------------------------------------------------
+// exclusive scan (int64), three phases, deterministic
+// ------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;  // per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *total) {
+    // v: this thread's value; returns exclusive prefix inside the block
+    __shared__ int64_t warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int64_t s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t n = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += n;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    int64_t base = w > 0 ? warp_sums[w - 1] : 0;
+    if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+    int64_t r = base + incl - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const int64_t *__restrict__ in, int64_t n,
+                                                               int64_t *__restrict__ tile_sums) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t s = 0;
+    for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_THREADS) {
+        int64_t k = base + i;
+        if (k < n) s += in[k];
+    }
+    int64_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets(int64_t *__restrict__ tile_sums, int64_t n_tiles,
+                                                                  int64_t *__restrict__ grand_total) {
+    // single block: in-place exclusive scan of tile_sums
+    int64_t carry = 0;
+    for (int64_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+        int64_t k = base + threadIdx.x;
+        int64_t v = k < n_tiles ? tile_sums[k] : 0;
+        int64_t total;
+        int64_t ex = block_exclusive_scan(v, &total);
+        if (k < n_tiles) tile_sums[k] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const int64_t *__restrict__ in, int64_t n,
+                                                           const int64_t *__restrict__ tile_offsets,
+                                                           int64_t *__restrict__ out) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t v[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t k = base + i;
+        v[i] = k < n ? in[k] : 0;
+        s += v[i];
+    }
+    int64_t ex = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t k = base + i;
+        if (k < n) out[k] = ex;
+        ex += v[i];
+    }
+}
+
+// ------------------------------------------------------------------------
+// sorted flat row ids -> rowptr
+// ------------------------------------------------------------------------
+__global__ void rowptr_from_rows(const int64_t *__restrict__ rows, int64_t nnz, int64_t n_rows,
+                                 int64_t *__restrict__ rowptr) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nnz) return;
+    int64_t prev = k == 0 ? -1 : rows[k - 1];
+    int64_t cur = k == nnz ? n_rows : rows[k];
+    for (int64_t r = prev + 1; r <= cur; ++r) rowptr[r] = k;
+}
+
+// ------------------------------------------------------------------------
+// merge: one warp per output row (t, i).  Lane l < b walks row i of source
+// slice halo + t - l.  Every step emits the smallest pending column; lanes
+// whose head equals it contribute w*val (fp64) and advance.  Outputs are
+// staged one per lane and flushed 32 at a time (coalesced).
+// ------------------------------------------------------------------------
+template <bool COUNT_ONLY, typename VT>
+__global__ void __launch_bounds__(256) merge_rows(const int64_t *__restrict__ in_rowptr,
+                                                  const int32_t *__restrict__ in_col, const VT *__restrict__ in_val,
+                                                  int T_out, int halo, int64_t N, const double *__restrict__ band_w,
+                                                  int b, int64_t *__restrict__ out_counts,
+                                                  const int64_t *__restrict__ out_rowptr,
+                                                  int32_t *__restrict__ out_col, VT *__restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_out_rows = (int64_t)T_out * N;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_out_rows;
+         row += warps_total) {
+        const int t = (int)(row / N);
+        const int64_t i = row - (int64_t)t * N;
+        int64_t p = 0, e = 0;
+        double w = 0.0;
+        if (lane < b) {
+            const int s = halo + t - lane;
+            w = band_w[(int64_t)t * b + lane];
+            if (s >= 0 && w != 0.0) {
+                p = in_rowptr[(int64_t)s * N + i];
+                e = in_rowptr[(int64_t)s * N + i + 1];
+            }
+        }
+        int cur = p < e ? in_col[p] : INT_MAX;
+        int64_t count = 0;
+        int64_t obase = COUNT_ONLY ? 0 : out_rowptr[row];
+        int32_t st_col = 0;
+        VT st_val = 0;
+        while (true) {
+            const int m = __reduce_min_sync(0xffffffffu, cur);
+            if (m == INT_MAX) break;
+            const bool hit = cur == m;
+            if (!COUNT_ONLY) {
+                double c = hit ? w * (double)in_val[p] : 0.0;
+                // fixed-order tree sum: deterministic
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (lane == (int)(count & 31)) {
+                    st_col = m;
+                    st_val = (VT)c;
+                }
+                if ((count & 31) == 31) {
+                    out_col[obase + count - 31 + lane] = st_col;
+                    out_val[obase + count - 31 + lane] = st_val;
+                }
+            }
+            if (hit) {
+                ++p;
+                cur = p < e ? in_col[p] : INT_MAX;
+            }
+            ++count;
+        }
+        if (COUNT_ONLY) {
+            if (lane == 0) out_counts[row] = count;
+        } else {
+            const int rem = (int)(count & 31);
+            if (lane < rem) {
+                out_col[obase + count - rem + lane] = st_col;
+                out_val[obase + count - rem + lane] = st_val;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------
+// per-slice transpose
+// ------------------------------------------------------------------------
+__global__ void transpose_count(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t N,
+                                int64_t n_rows, unsigned long long *__restrict__ counts) {
+    // warp per row so the col reads are coalesced
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
+        const int64_t tbase = (row / N) * N;
+        const int64_t s = rowptr[row], e = rowptr[row + 1];
+        for (int64_t k = s + lane; k < e; k += 32) atomicAdd(&counts[tbase + col[k]], 1ULL);
+    }
+}
+
+struct __align__(8) RowVal {
+    int32_t row;
+    float val;
+};
+
+__global__ void transpose_fill(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                               const float *__restrict__ val, int64_t N, int64_t n_rows,
+                               unsigned long long *__restrict__ cursor, RowVal *__restrict__ tmp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
+        const int64_t t = row / N;
+        const int64_t tbase = t * N;
+        const int32_t i = (int32_t)(row - tbase);
+        const int64_t s = rowptr[row], e = rowptr[row + 1];
+        for (int64_t k = s + lane; k < e; k += 32) {
+            unsigned long long pos = atomicAdd(&cursor[tbase + col[k]], 1ULL);
+            RowVal rv;
+            rv.row = i;
+            rv.val = val[k];
+            tmp[pos] = rv;
+        }
+    }
+}
+
+// rank sort of every transposed row (keys are unique inside a row): restores
+// ascending order so the backward SpMM sums in a reproducible order.
+__global__ void transpose_rank_sort(const int64_t *__restrict__ t_rowptr, const RowVal *__restrict__ tmp,
+                                    int64_t n_rows, int32_t *__restrict__ t_col, float *__restrict__ t_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
+        const int64_t s = t_rowptr[row], e = t_rowptr[row + 1];
+        const int64_t len = e - s;
+        if (len <= 32) {
+            RowVal mine;
+            mine.row = INT_MAX;
+            mine.val = 0.f;
+            if (lane < len) mine = tmp[s + lane];
+            int rank = 0;
+            for (int j = 0; j < (int)len; ++j) {
+                int kj = __shfl_sync(0xffffffffu, mine.row, j);
+                rank += kj < mine.row;
+            }
+            if (lane < len) {
+                t_col[s + rank] = mine.row;
+                t_val[s + rank] = mine.val;
+            }
+        } else {
+            for (int64_t a = lane; a < len; a += 32) {
+                RowVal mine = tmp[s + a];
+                int64_t rank = 0;
+                for (int64_t j = 0; j < len; ++j) rank += tmp[s + j].row < mine.row;
+                t_col[s + rank] = mine.row;
+                t_val[s + rank] = mine.val;
+            }
+        }
+    }
+}
+
+static int grid_for_warps(int64_t n_warps, int threads) {
+    int64_t blocks = ceil_div(n_warps * 32, threads);
+    int64_t cap = (int64_t)sm_count() * 32;  // persistent-ish: grid-stride beyond this
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace tmgcn
+
+using namespace tmgcn;
+
+extern "C" {
+
+size_t tmgcn_scan_ws_bytes(int64_t n) { return (size_t)(ceil_div(n > 0 ? n : 1, SCAN_TILE) + 1) * sizeof(int64_t); }
+
+int tmgcn_exclusive_scan_i64(const int64_t *counts, int64_t *out, int64_t n, void *ws, void *stream) {
+    TMGCN_REQUIRE(n >= 0, "scan: n < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        TMGCN_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t), st));
+        return 0;
+    }
+    TMGCN_REQUIRE(counts && out && ws, "scan: null pointer");
+    int64_t *tile_sums = (int64_t *)ws;
+    const int64_t n_tiles = ceil_div(n, SCAN_TILE);
+    scan_tile_sums<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums);
+    if (after_launch("scan_tile_sums")) return 1;
+    scan_tile_offsets<<<1, SCAN_THREADS, 0, st>>>(tile_sums, n_tiles, out + n);
+    if (after_launch("scan_tile_offsets")) return 1;
+    scan_apply<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums, out);
+    return after_launch("scan_apply");
+}
+
+int tmgcn_rowptr_from_sorted_rows(const int64_t *flat_row, int64_t nnz, int64_t n_rows, int64_t *rowptr,
+                                  void *stream) {
+    TMGCN_REQUIRE(nnz >= 0 && n_rows >= 0 && rowptr, "rowptr_from_sorted_rows: bad arguments");
+    const int threads = 256;
+    rowptr_from_rows<<<(unsigned)ceil_div(nnz + 1, threads), threads, 0, (cudaStream_t)stream>>>(flat_row, nnz,
+                                                                                                 n_rows, rowptr);
+    return after_launch("rowptr_from_rows");
+}
+
+static int check_band(int T_out, int halo, int64_t N, int b) {
+    TMGCN_REQUIRE(T_out >= 0 && N >= 0, "mtransform: negative size");
+    TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform: band width b=%d outside [1, 32]", b);
+    TMGCN_REQUIRE(halo >= 0, "mtransform: negative halo");
+    return 0;
+}
+
+int tmgcn_mtransform_sparse_plan(const int64_t *in_rowptr, const int32_t *in_col, int T_out, int halo, int64_t N,
+                                 const double *band_w, int b, int64_t *out_counts, void *stream) {
+    if (check_band(T_out, halo, N, b)) return 1;
+    if ((int64_t)T_out * N == 0) return 0;
+    TMGCN_REQUIRE(in_rowptr && band_w && out_counts, "mtransform_sparse_plan: null pointer");
+    const int threads = 256;
+    merge_rows<true, float><<<grid_for_warps((int64_t)T_out * N, threads), threads, 0, (cudaStream_t)stream>>>(
+        in_rowptr, in_col, nullptr, T_out, halo, N, band_w, b, out_counts, nullptr, nullptr, nullptr);
+    return after_launch("merge_rows<count>");
+}
+
+int tmgcn_mtransform_sparse_run(const int64_t *in_rowptr, const int32_t *in_col, const void *in_val, int T_out,
+                                int halo, int64_t N, const double *band_w, int b, const int64_t *out_rowptr,
+                                int32_t *out_col, void *out_val, int val_is_f64, void *stream) {
+    if (check_band(T_out, halo, N, b)) return 1;
+    if ((int64_t)T_out * N == 0) return 0;
+    TMGCN_REQUIRE(in_rowptr && band_w && out_rowptr, "mtransform_sparse_run: null pointer");
+    const int threads = 256;
+    const int grid = grid_for_warps((int64_t)T_out * N, threads);
+    if (val_is_f64)
+        merge_rows<false, double><<<grid, threads, 0, (cudaStream_t)stream>>>(
+            in_rowptr, in_col, (const double *)in_val, T_out, halo, N, band_w, b, nullptr, out_rowptr, out_col,
+            (double *)out_val);
+    else
+        merge_rows<false, float><<<grid, threads, 0, (cudaStream_t)stream>>>(
+            in_rowptr, in_col, (const float *)in_val, T_out, halo, N, band_w, b, nullptr, out_rowptr, out_col,
+            (float *)out_val);
+    return after_launch("merge_rows<fill>");
+}
+
+size_t tmgcn_csr_transpose_ws_bytes(int64_t n_rows, int64_t nnz) {
+    return (size_t)nnz * sizeof(RowVal) + (size_t)n_rows * sizeof(int64_t);
+}
+
+int tmgcn_csr_transpose_plan(const int64_t *rowptr, const int32_t *col, int T, int64_t N, int64_t *counts,
+                             void *stream) {
+    const int64_t n_rows = (int64_t)T * N;
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(rowptr && counts, "csr_transpose_plan: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    TMGCN_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_rows * sizeof(int64_t), st));
+    const int threads = 256;
+    transpose_count<<<grid_for_warps(n_rows, threads), threads, 0, st>>>(rowptr, col, N, n_rows,
+                                                                         (unsigned long long *)counts);
+    return after_launch("transpose_count");
+}
+
+int tmgcn_csr_transpose_run(const int64_t *rowptr, const int32_t *col, const float *val, int T, int64_t N,
+                            const int64_t *t_rowptr, int32_t *t_col, float *t_val, void *ws, void *stream) {
+    const int64_t n_rows = (int64_t)T * N;
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(rowptr && t_rowptr && ws, "csr_transpose_run: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *cursor = (unsigned long long *)ws;
+    RowVal *tmp = (RowVal *)((char *)ws + (size_t)n_rows * sizeof(int64_t));
+    TMGCN_CUDA(cudaMemcpyAsync(cursor, t_rowptr, (size_t)n_rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    const int threads = 256;
+    const int grid = grid_for_warps(n_rows, threads);
+    transpose_fill<<<grid, threads, 0, st>>>(rowptr, col, val, N, n_rows, cursor, tmp);
+    if (after_launch("transpose_fill")) return 1;
+    transpose_rank_sort<<<grid, threads, 0, st>>>(t_rowptr, tmp, n_rows, t_col, t_val);
+    return after_launch("transpose_rank_sort");
+}
+
+}  // extern "C"

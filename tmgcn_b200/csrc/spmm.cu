@@ -1,0 +1,181 @@
+// (d) facewise SpMM  y[t] = act( A~[t] . x[t] ), all T slices in one launch.
+//
+// ref: the per-slice loop `AtXt[k] = t.sparse.mm(At[k], Xt[k])` (ehf:205-207,
+// ehf:309-311) and compute_AX (ehf:301-305, ehf:469-473).  The backward
+// dX[t] = A~[t]^T . dY[t] is this same kernel on the transposed CSR.
+//
+// HBM-bound gather: per stored entry one 4*F-byte row of x is fetched.  A group
+// of G lanes (G*VEC >= F, VEC-wide vector loads) owns one CSR row, so a gathered
+// feature row is one fully coalesced request (512 B at F=128 with G=32,
+// VEC=4).  The group loads G (col, val) pairs at once (coalesced) and
+// broadcasts them with shuffles; the gathers are issued UNROLL at a time so a
+// warp keeps UNROLL independent 512 B requests in flight.  Rows are taken
+// grid-stride by a grid that is a multiple of the SM count.
+#include "common.cuh"
+
+namespace tmgcn {
+
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> {
+    using T = float4;
+};
+template <>
+struct VecT<2> {
+    using T = float2;
+};
+template <>
+struct VecT<1> {
+    using T = float;
+};
+
+__device__ __forceinline__ void axpy(float4 &a, float s, const float4 &x) {
+    a.x = fmaf(s, x.x, a.x);
+    a.y = fmaf(s, x.y, a.y);
+    a.z = fmaf(s, x.z, a.z);
+    a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ void axpy(float2 &a, float s, const float2 &x) {
+    a.x = fmaf(s, x.x, a.x);
+    a.y = fmaf(s, x.y, a.y);
+}
+__device__ __forceinline__ void axpy(float &a, float s, const float &x) { a = fmaf(s, x, a); }
+__device__ __forceinline__ void vzero(float4 &a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vzero(float2 &a) { a = make_float2(0.f, 0.f); }
+__device__ __forceinline__ void vzero(float &a) { a = 0.f; }
+template <int ACT>
+__device__ __forceinline__ void vact(float4 &a) {
+    a.x = act_apply<ACT>(a.x);
+    a.y = act_apply<ACT>(a.y);
+    a.z = act_apply<ACT>(a.z);
+    a.w = act_apply<ACT>(a.w);
+}
+template <int ACT>
+__device__ __forceinline__ void vact(float2 &a) {
+    a.x = act_apply<ACT>(a.x);
+    a.y = act_apply<ACT>(a.y);
+}
+template <int ACT>
+__device__ __forceinline__ void vact(float &a) {
+    a = act_apply<ACT>(a);
+}
+
+template <int VEC, int G, int ACT>
+__global__ void __launch_bounds__(256) spmm_rows(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                 const float *__restrict__ val, const float *__restrict__ x,
+                                                 float *__restrict__ y, int64_t n_rows, int64_t N, int F) {
+    using VT = typename VecT<VEC>::T;
+    constexpr int UNROLL = 8 < G ? 8 : G;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);  // lane inside the group
+    const int64_t groups_total = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int Fv = F / VEC;
+    // iterate in lock-step per warp so the shuffles stay convergent
+    const int64_t n_iter = ceil_div_dev(n_rows, groups_total);
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t row = g0 + it * groups_total;
+        const bool live = row < n_rows;
+        int64_t s = 0, e = 0, xbase = 0;
+        if (live) {
+            s = rowptr[row];
+            e = rowptr[row + 1];
+            xbase = (row / N) * N * (int64_t)Fv;  // first vector of this slice of x
+        }
+        const int len = (int)(e - s);
+        const int maxlen = G == 32 ? len : __reduce_max_sync(0xffffffffu, len);
+        for (int fb = 0; fb < Fv; fb += G) {  // uniform trip count: shuffles stay convergent
+            const int f0 = fb + gl;
+            const bool fact = f0 < Fv;
+            VT acc;
+            vzero(acc);
+            const VT *xv = reinterpret_cast<const VT *>(x) + xbase + f0;
+            for (int base = 0; base < maxlen; base += G) {
+                int c = 0;
+                float v = 0.f;
+                if (base + gl < len) {
+                    c = col[s + base + gl];
+                    v = val[s + base + gl];
+                }
+                const int cnt = min(G, maxlen - base);
+                for (int j0 = 0; j0 < cnt; j0 += UNROLL) {
+                    VT xs[UNROLL];
+                    float vs[UNROLL];
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u) {
+                        const int j = j0 + u;
+                        const int cj = __shfl_sync(0xffffffffu, c, j & (G - 1), G);
+                        vs[u] = __shfl_sync(0xffffffffu, v, j & (G - 1), G);
+                        const bool ok = fact && (base + j < len) && (j < cnt);
+                        if (ok)
+                            xs[u] = __ldg(xv + (int64_t)cj * Fv);
+                        else {
+                            vzero(xs[u]);
+                            vs[u] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u) axpy(acc, vs[u], xs[u]);
+                }
+            }
+            if (live && fact) {
+                vact<ACT>(acc);
+                reinterpret_cast<VT *>(y)[row * (int64_t)Fv + f0] = acc;
+            }
+        }
+    }
+}
+
+template <int VEC, int G>
+static int launch_spmm_act(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y,
+                           int64_t n_rows, int64_t N, int F, int act, cudaStream_t st) {
+    const int threads = 256;
+    const int64_t groups_per_block = threads / G;
+    int64_t blocks = ceil_div(n_rows, groups_per_block);
+    const int64_t cap = (int64_t)sm_count() * 8 * 8;  // 8 resident CTAs/SM x 8 waves, then grid-stride
+    if (blocks > cap) blocks = cap;
+    const unsigned grid = (unsigned)blocks;
+#define TMGCN_LAUNCH(A)                                                                                  \
+    spmm_rows<VEC, G, A><<<grid, threads, 0, st>>>(rowptr, col, val, x, y, n_rows, N, F);               \
+    break;
+    switch (act) {
+        case TMGCN_ACT_NONE: TMGCN_LAUNCH(TMGCN_ACT_NONE)
+        case TMGCN_ACT_RELU: TMGCN_LAUNCH(TMGCN_ACT_RELU)
+        case TMGCN_ACT_LEAKY: TMGCN_LAUNCH(TMGCN_ACT_LEAKY)
+        case TMGCN_ACT_SELU: TMGCN_LAUNCH(TMGCN_ACT_SELU)
+        default: set_error("spmm: unknown activation %d", act); return 1;
+    }
+#undef TMGCN_LAUNCH
+    return after_launch("spmm_rows");
+}
+
+template <int VEC>
+static int launch_spmm_g(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y,
+                         int64_t n_rows, int64_t N, int F, int act, cudaStream_t st) {
+    const int fv = F / VEC;
+    if (fv <= 1) return launch_spmm_act<VEC, 1>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 2) return launch_spmm_act<VEC, 2>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 4) return launch_spmm_act<VEC, 4>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 8) return launch_spmm_act<VEC, 8>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 16) return launch_spmm_act<VEC, 16>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    return launch_spmm_act<VEC, 32>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+}
+
+}  // namespace tmgcn
+
+extern "C" int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y,
+                              int T, int64_t N, int F, int act, void *stream) {
+    using namespace tmgcn;
+    TMGCN_REQUIRE(T >= 0 && N >= 0 && F >= 1, "spmm: bad sizes T=%d N=%lld F=%d", T, (long long)N, F);
+    const int64_t n_rows = (int64_t)T * N;
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(rowptr && x && y, "spmm: null pointer");
+    TMGCN_REQUIRE(x != y, "spmm: in-place operation is not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+    const bool a8 = ((uintptr_t)x % 8 == 0) && ((uintptr_t)y % 8 == 0);
+    if (F % 4 == 0 && a16) return launch_spmm_g<4>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (F % 2 == 0 && a8) return launch_spmm_g<2>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    return launch_spmm_g<1>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+}

@@ -1,0 +1,191 @@
+// (b) dense M-transform  X~ = X x_3 M  as a streamed time stencil.
+//
+// ref: Xt = t.matmul(M, X.reshape(T, -1))  (ehf:204, ehf:308, ehf:346) -- the
+// reference multiplies by the dense T x T matrix; M is banded, so every output
+// slice is a weighted sum of the b previous input slices.
+//
+// Layout: a thread owns one float4 column of the (T, N*F) matrix and marches
+// through time keeping the last B-1+C inputs in a register ring, so each input
+// element is read from HBM exactly once and each output written once
+// (8*N*F bytes per slice, the algorithmic minimum).  Adjacent threads own
+// adjacent float4s: every load/store is a fully coalesced 512 B per warp.  The
+// band weights sit in shared memory (broadcast reads).  The time loop is unrolled
+// over the ring period R so every ring index is a compile-time constant, and the
+// C loads of a chunk are issued before they are consumed (C independent 16 B
+// loads in flight per thread).
+#include "common.cuh"
+
+namespace tmgcn {
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<4> {
+    using T = float4;
+};
+template <>
+struct Vec<1> {
+    using T = float;
+};
+
+__device__ __forceinline__ void fma_v(float4 &a, float w, const float4 &x) {
+    a.x = fmaf(w, x.x, a.x);
+    a.y = fmaf(w, x.y, a.y);
+    a.z = fmaf(w, x.z, a.z);
+    a.w = fmaf(w, x.w, a.w);
+}
+__device__ __forceinline__ void fma_v(float &a, float w, const float &x) { a = fmaf(w, x, a); }
+__device__ __forceinline__ void zero_v(float4 &a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void zero_v(float &a) { a = 0.f; }
+__device__ __forceinline__ float4 ld_v(const float4 *p) { return ld_stream_f4(p); }
+__device__ __forceinline__ float ld_v(const float *p) { return __ldg(p); }
+__device__ __forceinline__ void st_v(float4 *p, const float4 &v) { st_stream_f4(p, v); }
+__device__ __forceinline__ void st_v(float *p, const float &v) { *p = v; }
+
+constexpr int STENCIL_C = 4;  // loads in flight per thread
+constexpr int ring_size(int B) { return STENCIL_C * ((B - 1 + STENCIL_C + STENCIL_C - 1) / STENCIL_C); }
+
+// Shared-memory weight table with B rows of zero padding on both sides so the
+// kernels index it without bounds checks: sw[(t + B) * B + i] = M[t, t-i].
+template <int B>
+__device__ __forceinline__ void load_weights(float *sw, const float *__restrict__ band_w, int T_out, int b) {
+    const int total = (T_out + 2 * B) * B;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+        const int t = k / B - B, i = k % B;
+        sw[k] = (t >= 0 && t < T_out && i < b) ? band_w[t * b + i] : 0.f;
+    }
+    __syncthreads();
+}
+
+// FWD : y[t]  = sum_i w[t][i]       * x[halo + t - i]          (REVERSE = false)
+// BWD : gx[s] = sum_i w[s-halo+i][i] * gy[s - halo + i]         (REVERSE = true)
+// Both march over the T_in = halo + T_out slices of the LONG tensor (x / gx); the
+// forward walks it upwards reading x and writing y, the backward walks it
+// downwards reading gy and writing gx.
+template <int B, int V, bool REVERSE>
+__global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                      int T_out, int halo, int64_t n_vec,
+                                                      const float *__restrict__ band_w, int b) {
+    using VT = typename Vec<V>::T;
+    constexpr int C = STENCIL_C, R = ring_size(B);
+    extern __shared__ float sw[];
+    load_weights<B>(sw, band_w, T_out, b);
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_vec) return;
+    const VT *in = reinterpret_cast<const VT *>(src) + pos;
+    VT *out = reinterpret_cast<VT *>(dst) + pos;
+    const int T_in = halo + T_out;
+    VT ring[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) zero_v(ring[k]);
+
+    for (int u0 = 0; u0 < T_in; u0 += R) {
+#pragma unroll
+        for (int q = 0; q < R; q += C) {
+            if (u0 + q < T_in) {
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    const int u = u0 + q + k;  // step number
+                    if (!REVERSE) {
+                        // entering element: x[u]
+                        if (u < T_in) ring[q + k] = ld_v(in + (int64_t)u * n_vec);
+                    } else {
+                        // entering element: gy[t0], t0 = (T_in-1-u) - halo  (absent for the halo slices)
+                        const int t0 = T_in - 1 - u - halo;
+                        if (u < T_in) {
+                            if (t0 >= 0)
+                                ring[q + k] = ld_v(in + (int64_t)t0 * n_vec);
+                            else
+                                zero_v(ring[q + k]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    const int u = u0 + q + k;
+                    if (u < T_in) {
+                        VT acc;
+                        zero_v(acc);
+                        if (!REVERSE) {
+                            const int t = u - halo;
+                            if (t >= 0) {
+                                const float *w = sw + (t + B) * B;
+#pragma unroll
+                                for (int i = 0; i < B; ++i) fma_v(acc, w[i], ring[(q + k - i + 2 * R) % R]);
+                                st_v(out + (int64_t)t * n_vec, acc);
+                            }
+                        } else {
+                            const int s = T_in - 1 - u;
+                            const int t0 = s - halo;  // >= -halo >= -(B-1)
+#pragma unroll
+                            for (int i = 0; i < B; ++i)
+                                fma_v(acc, sw[(t0 + i + B) * B + i], ring[(q + k - i + 2 * R) % R]);
+                            st_v(out + (int64_t)s * n_vec, acc);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int B, int V, bool REVERSE>
+static int launch_stencil(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
+                          cudaStream_t st) {
+    const int64_t n_vec = NF / V;
+    const size_t smem = (size_t)(T_out + 2 * B) * B * sizeof(float);
+    TMGCN_REQUIRE(smem <= 200 * 1024, "mtransform_dense: T_out=%d too large for the weight table (b=%d)", T_out, b);
+    auto kern = stencil_kernel<B, V, REVERSE>;
+    if (smem > 48 * 1024) TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = 256;
+    kern<<<(unsigned)ceil_div(n_vec, threads), threads, smem, st>>>(src, dst, T_out, halo, n_vec, band_w, b);
+    return after_launch(REVERSE ? "stencil_bwd" : "stencil_fwd");
+}
+
+template <int V, bool REVERSE>
+static int dispatch_b(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
+                      cudaStream_t st) {
+#define TMGCN_CASE(BB) \
+    if (b <= BB) return launch_stencil<BB, V, REVERSE>(src, dst, T_out, halo, NF, band_w, b, st);
+    TMGCN_CASE(1)
+    TMGCN_CASE(2)
+    TMGCN_CASE(4)
+    TMGCN_CASE(6)
+    TMGCN_CASE(8)
+    TMGCN_CASE(10)
+    TMGCN_CASE(12)
+    TMGCN_CASE(16)
+    TMGCN_CASE(20)
+    TMGCN_CASE(24)
+    TMGCN_CASE(32)
+#undef TMGCN_CASE
+    set_error("mtransform_dense: band width b=%d > 32 unsupported", b);
+    return 1;
+}
+
+template <bool REVERSE>
+static int stencil_entry(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
+                         void *stream) {
+    TMGCN_REQUIRE(T_out >= 0 && NF >= 0 && halo >= 0, "mtransform_dense: negative size");
+    TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform_dense: band width b=%d outside [1, 32]", b);
+    TMGCN_REQUIRE(halo <= b - 1, "mtransform_dense: halo=%d exceeds b-1=%d", halo, b - 1);
+    if (NF == 0 || halo + T_out == 0) return 0;
+    TMGCN_REQUIRE(src && dst && band_w, "mtransform_dense: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec4 = (NF % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    if (vec4) return dispatch_b<4, REVERSE>(src, dst, T_out, halo, NF, band_w, b, st);
+    return dispatch_b<1, REVERSE>(src, dst, T_out, halo, NF, band_w, b, st);
+}
+
+}  // namespace tmgcn
+
+extern "C" {
+int tmgcn_mtransform_dense_fwd(const float *x_in, float *x_out, int T_out, int halo, int64_t NF,
+                               const float *band_w, int b, void *stream) {
+    return tmgcn::stencil_entry<false>(x_in, x_out, T_out, halo, NF, band_w, b, stream);
+}
+int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
+                               const float *band_w, int b, void *stream) {
+    return tmgcn::stencil_entry<true>(g_out, g_in, T_out, halo, NF, band_w, b, stream);
+}
+}

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's call surface for the hot path.
+
+Same names, argument meaning, dispatch rule and error behaviour as
+TensorGCN-master/embedding_help_functions.py (ehf) and the func_MProduct /
+create_matrix_M helpers -- backed by libtmgcn_b200.so instead of ATen CPU ops.
+
+Differences a caller can observe (all documented in INTEGRATION.md):
+  * results and parameters live on the current CUDA device (fp32);
+  * `use_Minv=True` and `condensed_W=False` raise NotImplementedError (no shipped
+    experiment uses them; SURVEY.md section 8f lists them as "next" rows).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ACT, Band, EdgePlan, SliceCSR
+
+
+# --------------------------------------------------------------------------
+# L2: M-product operators
+# --------------------------------------------------------------------------
+def create_matrix_M(T: int, no_diag: int, normalize: bool = False) -> torch.Tensor:
+    """Banded lower-triangular M, fp64 (T, T): M[t, t-i] = 1/(i+1), i < no_diag
+    (ref: SBM_our.py:88-96); `normalize=True` gives the row-normalised ones band
+    of ref: read_data.py:56-62.  Host-side helper (T*b numbers)."""
+    M = torch.zeros(T, T, dtype=torch.float64)
+    for i in range(min(no_diag, T)):
+        M.diagonal(-i).fill_(1.0 if normalize else 1.0 / (i + 1))
+    if normalize:
+        M = M / M.sum(dim=1, keepdim=True)
+    return M
+
+
+def func_MProduct(C: torch.Tensor, M: torch.Tensor, no_diag: Optional[int] = None) -> torch.Tensor:
+    """Sparse mode-3 product C x_3 M (ref: read_data.py:204-223).
+
+    C: sparse COO (T, N, N); M: (T, T) banded lower triangular.  Returns a
+    coalesced sparse COO tensor (int64 indices in (t, i, j) order, fp64 values)
+    on the CUDA device -- index-for-index what the reference's
+    `C_new.coalesce()` holds."""
+    assert C.size()[0] == M.size()[0]  # ref: read_data.py:205
+    T, N, N2 = C.shape
+    if N != N2:
+        raise ValueError("C must be T x N x N")
+    band = Band(M)
+    if no_diag is not None:
+        assert band.b <= no_diag  # ref: read_data.py:217
+    Cc = C if C.is_coalesced() else C.coalesce()
+    csr = SliceCSR.from_coo(Cc._indices(), Cc._values(), T, N, dtype=torch.float64)
+    out = ops.mtransform_sparse(csr, band)
+    idx, val = out.to_coo()
+    return torch.sparse_coo_tensor(idx, val, (T, N, N), is_coalesced=True)
+
+
+def split_slices(Ct: torch.Tensor) -> List[torch.Tensor]:
+    """T x N x N sparse COO -> list of T 2-D sparse COO matrices, the `At`
+    argument of the modules (ref: ehf:561-572, experiment_bitcoin_our.py:53-56)."""
+    Ct = Ct if Ct.is_coalesced() else Ct.coalesce()
+    T, N = Ct.shape[0], Ct.shape[1]
+    idx, val = Ct._indices(), Ct._values()
+    bounds = torch.searchsorted(idx[0].contiguous(), torch.arange(T + 1, device=idx.device))
+    out = []
+    for j in range(T):
+        a, b = int(bounds[j]), int(bounds[j + 1])
+        out.append(torch.sparse_coo_tensor(idx[1:3, a:b], val[a:b], (N, N), is_coalesced=True))
+    return out
+
+
+# --------------------------------------------------------------------------
+# L3: model modules
+# --------------------------------------------------------------------------
+def _act_name(nonlin2: str) -> str:
+    if nonlin2 not in ("relu", "leaky", "selu"):
+        raise ValueError('nonlin2 must be "relu", "leaky" or "selu"')  # ref: ehf:284-289
+    return nonlin2
+
+
+class _Base(nn.Module):
+    def _csr(self, A, N) -> SliceCSR:
+        """list-of-COO -> device CSR, cached by list identity."""
+        if isinstance(A, SliceCSR):
+            return A
+        cache = self.__dict__.setdefault("_csr_cache", {})
+        key = id(A)
+        hit = cache.get(key)
+        if hit is not None and hit[0] is A:
+            return hit[1]
+        csr = SliceCSR.from_slice_list(A, N)
+        cache[key] = (A, csr)
+        return csr
+
+    @staticmethod
+    def _x(X) -> torch.Tensor:
+        return X.detach().to(device=ops._dev(), dtype=torch.float32).contiguous()
+
+    @staticmethod
+    def _fresh(At, X, edges) -> bool:
+        # the reference's dispatch rule, verbatim semantics (ref: ehf:212, 316, 476)
+        return type(At) == list and type(X) == torch.Tensor and type(edges) == torch.Tensor
+
+    @staticmethod
+    def _param(*shape) -> nn.Parameter:
+        # drawn on the CPU generator in the reference's order, so a seed reproduces its init
+        return nn.Parameter(torch.randn(*shape).to(ops._dev()))
+
+
+class EmbeddingGCN(_Base):
+    """1-layer TM-GCN (ref: ehf:156-234)."""
+
+    def __init__(self, At, X, edges, M, hidden_feat=[2, 2], condensed_W=False, use_Minv=True):
+        super().__init__()
+        if use_Minv:
+            raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
+        if not condensed_W:
+            raise NotImplementedError("condensed_W=False is outside the accelerated path (SURVEY.md section 8f)")
+        self.M = M
+        self.band = Band(M)
+        self.use_Minv = use_Minv
+        self.T = X.shape[0]
+        self.N = X.shape[1]
+        self.F = [X.shape[-1]] + hidden_feat
+        self.W = self._param(self.F[0], self.F[1])
+        self.U = self._param(2 * self.F[1], self.F[2])
+        self.AtXt = self.compute_AtXt(At, X)                  # ref: ehf:195
+        self.edge_plan = EdgePlan(edges, self.N)              # ref: ehf:196-198
+
+    def compute_AtXt(self, At, X):
+        """(T, N, F) fp32 = facewise At[k] @ (M x_3 X)[k] (ref: ehf:203-208)."""
+        csr = self._csr(At, self.N)
+        with torch.no_grad():
+            return ops.spmm_raw(csr, ops.stencil_fwd(self._x(X), self.band))
+
+    def forward(self, At=None, X=None, edges=None):
+        if self._fresh(At, X, edges):
+            AtXt = self.compute_AtXt(At, X)
+            plan = EdgePlan(edges, self.N)
+        else:
+            AtXt, plan = self.AtXt, self.edge_plan
+        Y = ops.gemm_xw(AtXt, self.W)                         # ref: ehf:222
+        return ops.edge_readout(Y, self.U, plan)              # ref: ehf:228-232
+
+
+class EmbeddingGCN2(_Base):
+    """2-layer TM-GCN (ref: ehf:236-357)."""
+
+    def __init__(self, At, X, edges, M, hidden_feat=[2, 2, 2], condensed_W=False, use_Minv=True,
+                 apply_M_twice=False, apply_M_three_times=False, nonlin2="relu"):
+        super().__init__()
+        if use_Minv:
+            raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
+        if not condensed_W:
+            raise NotImplementedError("condensed_W=False is outside the accelerated path (SURVEY.md section 8f)")
+        self.At = At
+        self.M = M
+        self.band = Band(M)
+        self.use_Minv = use_Minv
+        self.apply_M_twice = apply_M_twice
+        self.apply_M_three_times = apply_M_three_times
+        self.T = X.shape[0]
+        self.N = X.shape[1]
+        self.F = [X.shape[-1]] + hidden_feat
+        self.W1 = self._param(self.F[0], self.F[1])
+        self.W2 = self._param(self.F[1], self.F[2])
+        self.U = self._param(self.F[2] * 2, self.F[3])
+        self.nonlin2 = _act_name(nonlin2)
+        self.At_csr = self._csr(At, self.N)
+        self.AtXt = self.compute_AtXt(At, X)
+        self.edge_plan = EdgePlan(edges, self.N)
+
+    def compute_AX(self, A, X):
+        """facewise A[k] @ X[k] (ref: ehf:301-305); differentiable w.r.t. X."""
+        return ops.spmm(self._csr(A, self.N), X)
+
+    def compute_AtXt(self, At, X):
+        """facewise At[k] @ (M x_3 X)[k] (ref: ehf:307-312); differentiable w.r.t. X
+        when X is a CUDA tensor that requires grad."""
+        csr = self._csr(At, self.N)
+        if X.is_cuda and X.requires_grad:
+            return ops.spmm(csr, ops.mtransform_dense(X, self.band))
+        with torch.no_grad():
+            return ops.spmm_raw(csr, ops.stencil_fwd(self._x(X), self.band))
+
+    def forward(self, At=None, X=None, edges=None):
+        if self._fresh(At, X, edges):
+            AtXt = self.compute_AtXt(At, X)
+            plan = EdgePlan(edges, self.N)
+        else:
+            AtXt, plan = self.AtXt, self.edge_plan
+        Y = ops.gemm_xw(AtXt, self.W1, self.nonlin2)          # layer 1 (ref: ehf:330-335)
+        if self.apply_M_twice:                                # ref: ehf:342-346
+            Z = ops.gemm_xw(ops.spmm(self.At_csr, ops.mtransform_dense(Y, self.band)), self.W2)
+            if self.apply_M_three_times:
+                Z = ops.mtransform_dense(Z, self.band)
+        else:                                                 # ref: ehf:347-349
+            Z = ops.gemm_xw(ops.spmm(self.At_csr, Y), self.W2)
+        return ops.edge_readout(Z, self.U, plan)              # ref: ehf:351-355
+
+
+class EmbeddingKWGCN(_Base):
+    """Static-GCN baseline, 1 or 2 layers (ref: ehf:425-497)."""
+
+    def __init__(self, A, X, edges, hidden_feat=[2, 2], nonlin2="relu"):
+        super().__init__()
+        self.no_layers = len(hidden_feat) - 1
+        self.T = len(A)
+        self.N = X.shape[1]
+        self.A = A
+        self.F = [X.shape[-1]] + hidden_feat
+        if self.no_layers == 2:                               # reference draws W2 first (ehf:451-453)
+            self.W2 = self._param(self.F[1], self.F[2])
+        self.W1 = self._param(self.F[0], self.F[1])
+        self.U = self._param(self.F[-2] * 2, self.F[-1])
+        self.nonlin2 = _act_name(nonlin2)
+        self.A_csr = self._csr(A, self.N)
+        self.edge_plan = EdgePlan(edges, self.N)
+        self.AX = self.compute_AX(A, X)
+
+    def compute_AX(self, A, X):
+        csr = self._csr(A, self.N)
+        if X.is_cuda and X.requires_grad:
+            return ops.spmm(csr, X)
+        with torch.no_grad():
+            return ops.spmm_raw(csr, self._x(X))
+
+    def forward(self, A=None, X=None, edges=None):
+        if self._fresh(A, X, edges):
+            AX = self.compute_AX(A, X)
+            plan = EdgePlan(edges, self.N)
+        else:
+            AX, plan = self.AX, self.edge_plan
+        if self.no_layers == 2:                               # ref: ehf:486-487
+            Y = ops.gemm_xw(AX, self.W1, self.nonlin2)
+            Z = ops.gemm_xw(ops.spmm(self.A_csr, Y), self.W2)
+        else:
+            Z = ops.gemm_xw(AX, self.W1)
+        return ops.edge_readout(Z, self.U, plan)
+
+
+class TMGCNLayer(nn.Module):
+    """One TM-GCN propagation layer with readout -- the unit the benchmark times
+    (SURVEY.md section 8d): H -> M x_3 H -> A~_t . H~_t -> act(. W) -> edge readout . U.
+    Equals layer 2 of EmbeddingGCN2(apply_M_twice=True) plus readout/classifier
+    (ref: ehf:342-344, 351-355)."""
+
+    def __init__(self, At: SliceCSR, band: Band, edge_plan: EdgePlan, W: torch.Tensor, U: torch.Tensor, act=None,
+                 t0: int = 0, t1: Optional[int] = None, halo: int = 0):
+        super().__init__()
+        self.At, self.band, self.edge_plan, self.act = At, band, edge_plan, act
+        self.t0, self.t1, self.halo = t0, (band.T if t1 is None else t1), halo
+        self.W = nn.Parameter(W.detach().to(ops._dev(), torch.float32).contiguous())
+        self.U = nn.Parameter(U.detach().to(ops._dev(), torch.float32).contiguous())
+
+    def forward(self, H: torch.Tensor) -> torch.Tensor:
+        Ht = ops.mtransform_dense(H, self.band, self.t0, self.t1, self.halo)
+        Y = ops.gemm_xw(ops.spmm(self.At, Ht), self.W, self.act)
+        return ops.edge_readout(Y, self.U, self.edge_plan)

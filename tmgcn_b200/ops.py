@@ -1,0 +1,453 @@
+"""Tensor-facing wrappers over the C ABI (include/tmgcn.h) and their autograd wiring.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all
+arithmetic on the hot path happens in libtmgcn_b200.so.  There is no CPU
+fallback: tensors are moved to the current CUDA device and the library raises if
+it cannot run.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "relu": 1, "leaky": 2, "selu": 3}
+
+
+def _dev() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("tmgcn_b200 needs a CUDA device (no CPU fallback exists)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "tmgcn: expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(device=_dev(), dtype=torch.float32).contiguous()
+
+
+def _ws(nbytes: int) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=_dev())
+
+
+# --------------------------------------------------------------------------
+# integer helpers
+# --------------------------------------------------------------------------
+def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
+    """int64 counts[n] -> int64 out[n+1] (out[n] = total)."""
+    lib = _lib.load()
+    counts = counts.to(device=_dev(), dtype=torch.int64).contiguous()
+    n = counts.numel()
+    out = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    ws = _ws(lib.tmgcn_scan_ws_bytes(n))
+    _lib.check(lib.tmgcn_exclusive_scan_i64(_p(counts), _p(out), n, _p(ws), _stream()))
+    return out
+
+
+class SliceCSR:
+    """T x N x N sparse tensor as one CSR over T*N rows (see include/tmgcn.h)."""
+
+    def __init__(self, T: int, N: int, rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor):
+        self.T, self.N = int(T), int(N)
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self._t: Optional["SliceCSR"] = None
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+    def slice_nnz(self) -> torch.Tensor:
+        rp = self.rowptr[:: self.N] if self.N > 0 else self.rowptr
+        return rp[1:] - rp[:-1]
+
+    @staticmethod
+    def from_coo(idx: torch.Tensor, val: torch.Tensor, T: int, N: int, dtype=torch.float32) -> "SliceCSR":
+        """idx (3, nnz) int64 in coalesced (t, i, j) order
+        (replaces the per-slice masking of ref: ehf:561-572)."""
+        lib = _lib.load()
+        dev = _dev()
+        idx = idx.to(dev)
+        flat = (idx[0] * N + idx[1]).contiguous()
+        col = idx[2].to(torch.int32).contiguous()
+        val = val.to(device=dev, dtype=dtype).contiguous()
+        rowptr = torch.empty(T * N + 1, dtype=torch.int64, device=dev)
+        _lib.check(lib.tmgcn_rowptr_from_sorted_rows(_p(flat), flat.numel(), T * N, _p(rowptr), _stream()))
+        return SliceCSR(T, N, rowptr, col, val)
+
+    @staticmethod
+    def from_slice_list(slices: Sequence[torch.Tensor], N: int, dtype=torch.float32) -> "SliceCSR":
+        """Python list of T 2-D sparse COO matrices (the reference's `At` argument,
+        ref: experiment_bitcoin_our.py:53-56) -> device CSR-of-slices."""
+        ts, rs, cs, vs = [], [], [], []
+        for t, A in enumerate(slices):
+            if A.layout != torch.sparse_coo:
+                raise TypeError("every slice must be a sparse COO tensor")
+            A = A if A.is_coalesced() else A.coalesce()
+            ij = A._indices()
+            if ij.numel() and int(ij.max()) >= N:
+                raise ValueError(f"slice {t} has an index >= N={N}")
+            ts.append(torch.full((ij.shape[1],), t, dtype=torch.int64, device=ij.device))
+            rs.append(ij[0])
+            cs.append(ij[1])
+            vs.append(A._values())
+        if not ts:
+            idx = torch.zeros(3, 0, dtype=torch.int64)
+            val = torch.zeros(0, dtype=torch.float64)
+        else:
+            idx = torch.stack([torch.cat(ts), torch.cat(rs), torch.cat(cs)])
+            val = torch.cat(vs)
+        return SliceCSR.from_coo(idx, val, len(slices), N, dtype)
+
+    def row_ids(self) -> torch.Tensor:
+        counts = self.rowptr[1:] - self.rowptr[:-1]
+        return torch.repeat_interleave(torch.arange(self.T * self.N, device=self.rowptr.device), counts)
+
+    def to_coo(self):
+        """-> idx (3, nnz) int64 in coalesced order, val."""
+        r = self.row_ids()
+        idx = torch.stack([r // self.N, r % self.N, self.col.to(torch.int64)])
+        return idx, self.val
+
+    def transpose(self) -> "SliceCSR":
+        """Per-slice transpose (cached) for the backward SpMM."""
+        if self._t is not None:
+            return self._t
+        if self.val.dtype != torch.float32:
+            raise TypeError("transpose: fp32 values only")
+        lib = _lib.load()
+        dev = self.rowptr.device
+        n_rows = self.T * self.N
+        counts = torch.empty(n_rows, dtype=torch.int64, device=dev)
+        _lib.check(lib.tmgcn_csr_transpose_plan(_p(self.rowptr), _p(self.col), self.T, self.N, _p(counts), _stream()))
+        t_rowptr = exclusive_scan(counts)
+        del counts
+        t_col = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+        t_val = torch.empty(self.nnz, dtype=torch.float32, device=dev)
+        ws = _ws(lib.tmgcn_csr_transpose_ws_bytes(n_rows, self.nnz))
+        _lib.check(lib.tmgcn_csr_transpose_run(_p(self.rowptr), _p(self.col), _p(self.val), self.T, self.N,
+                                               _p(t_rowptr), _p(t_col), _p(t_val), _p(ws), _stream()))
+        self._t = SliceCSR(self.T, self.N, t_rowptr, t_col, t_val)
+        self._t._t = self
+        return self._t
+
+
+# --------------------------------------------------------------------------
+# M as a band
+# --------------------------------------------------------------------------
+class Band:
+    """Banded lower-triangular M (ref: SBM_our.py:88-96, read_data.py:56-62):
+    w[t, i] = M[t, t-i].  `rows` selects the output slices a rank owns."""
+
+    def __init__(self, M: torch.Tensor, max_b: int = 32):
+        M = torch.as_tensor(M).detach().to("cpu", torch.float64)
+        if M.dim() != 2 or M.shape[0] != M.shape[1]:
+            raise ValueError("M must be a square matrix")
+        if torch.count_nonzero(torch.triu(M, 1)) != 0:
+            raise NotImplementedError("M must be lower triangular (banded); dense M / inv(M) is out of scope")
+        T = M.shape[0]
+        nz = torch.nonzero(M)
+        b = int((nz[:, 0] - nz[:, 1]).max()) + 1 if nz.numel() else 1
+        if b > max_b:
+            raise NotImplementedError(f"band width {b} > {max_b} unsupported")
+        w = torch.zeros(T, b, dtype=torch.float64)
+        for i in range(b):
+            w[i:, i] = torch.diagonal(M, -i)
+        self.T, self.b, self.w = T, b, w
+        self._dev = {}
+
+    def device_weights(self, t0: int, t1: int, dtype) -> torch.Tensor:
+        key = (t0, t1, dtype, torch.cuda.current_device())
+        if key not in self._dev:
+            self._dev[key] = self.w[t0:t1].to(device=_dev(), dtype=dtype).contiguous()
+        return self._dev[key]
+
+
+def mtransform_sparse(csr: SliceCSR, band: Band, t0: int = 0, t1: Optional[int] = None, halo: int = 0) -> SliceCSR:
+    """A~ = A x_3 M on CSR-of-slices (ref: func_MProduct, read_data.py:204-223).
+    `csr` holds input slices [t0 - halo, t1); the result holds output slices [t0, t1)."""
+    lib = _lib.load()
+    t1 = band.T if t1 is None else t1
+    T_out = t1 - t0
+    if csr.T != T_out + halo:
+        raise ValueError(f"input has {csr.T} slices, expected halo + T_out = {halo + T_out}")
+    f64 = csr.val.dtype == torch.float64
+    w = band.device_weights(t0, t1, torch.float64)
+    N = csr.N
+    dev = csr.rowptr.device
+    counts = torch.empty(T_out * N, dtype=torch.int64, device=dev)
+    _lib.check(lib.tmgcn_mtransform_sparse_plan(_p(csr.rowptr), _p(csr.col), T_out, halo, N, _p(w), band.b,
+                                                _p(counts), _stream()))
+    rowptr = exclusive_scan(counts)
+    del counts
+    nnz = int(rowptr[-1].item())
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    val = torch.empty(nnz, dtype=csr.val.dtype, device=dev)
+    _lib.check(lib.tmgcn_mtransform_sparse_run(_p(csr.rowptr), _p(csr.col), _p(csr.val), T_out, halo, N, _p(w),
+                                               band.b, _p(rowptr), _p(col), _p(val), 1 if f64 else 0, _stream()))
+    return SliceCSR(T_out, N, rowptr, col, val)
+
+
+# --------------------------------------------------------------------------
+# raw (non-autograd) kernels
+# --------------------------------------------------------------------------
+def stencil_fwd(x: torch.Tensor, band: Band, t0: int = 0, t1: Optional[int] = None, halo: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    t1 = band.T if t1 is None else t1
+    T_out = t1 - t0
+    assert x.shape[0] == T_out + halo, "x must hold halo + T_out slices"
+    NF = x[0].numel() if x.shape[0] else 0
+    out = torch.empty((T_out,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    w = band.device_weights(t0, t1, torch.float32)
+    _lib.check(lib.tmgcn_mtransform_dense_fwd(_p(x), _p(out), T_out, halo, NF, _p(w), band.b, _stream()))
+    return out
+
+
+def stencil_bwd(g: torch.Tensor, band: Band, t0: int = 0, t1: Optional[int] = None, halo: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    t1 = band.T if t1 is None else t1
+    T_out = t1 - t0
+    assert g.shape[0] == T_out
+    NF = g[0].numel() if g.shape[0] else 0
+    out = torch.empty((T_out + halo,) + tuple(g.shape[1:]), dtype=torch.float32, device=g.device)
+    w = band.device_weights(t0, t1, torch.float32)
+    _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(g), _p(out), T_out, halo, NF, _p(w), band.b, _stream()))
+    return out
+
+
+def spmm_raw(csr: SliceCSR, x: torch.Tensor, act: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.dim() == 3 and x.shape[0] == csr.T and x.shape[1] == csr.N, "x must be (T, N, F)"
+    if csr.val.dtype != torch.float32:
+        raise TypeError("spmm: fp32 CSR values only")
+    y = torch.empty_like(x) if out is None else out
+    _lib.check(lib.tmgcn_spmm_fwd(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(x), _p(y), csr.T, csr.N,
+                                  x.shape[2], act, _stream()))
+    return y
+
+
+def gemm_fwd_raw(p: torch.Tensor, w: torch.Tensor, act: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    K, Nf = w.shape
+    R = p.numel() // K
+    y = torch.empty(tuple(p.shape[:-1]) + (Nf,), dtype=torch.float32, device=p.device)
+    _lib.check(lib.tmgcn_gemm_xw_fwd(_p(p), _p(w), _p(y), R, K, Nf, act, _stream()))
+    return y
+
+
+def gemm_bwd_raw(p, w, y, dy, act: int, need_dp: bool = True, need_dw: bool = True):
+    lib = _lib.load()
+    K, Nf = w.shape
+    R = dy.numel() // Nf
+    dp = torch.empty(tuple(dy.shape[:-1]) + (K,), dtype=torch.float32, device=dy.device) if need_dp else None
+    dw = torch.empty_like(w) if need_dw else None
+    ws = _ws(lib.tmgcn_gemm_dw_ws_bytes(K, Nf)) if need_dw else None
+    _lib.check(lib.tmgcn_gemm_dw_dx_bwd(_p(p), _p(w), _p(y), _p(dy), _p(dp), _p(dw), R, K, Nf, act, _p(ws),
+                                        _stream()))
+    return dp, dw
+
+
+class EdgePlan:
+    """Flat endpoint ids (ref: ehf:196-198) plus, lazily, the incidence list that
+    makes the backward scatter-add deterministic."""
+
+    def __init__(self, edges: torch.Tensor, N: int, t_offset: int = 0):
+        lib = _lib.load()
+        edges = edges.to(device=_dev(), dtype=torch.int64).contiguous()
+        assert edges.dim() == 2 and edges.shape[0] == 3, "edges must be (3, E): time, src, dst"
+        self.E = int(edges.shape[1])
+        self.src = torch.empty(self.E, dtype=torch.int64, device=edges.device)
+        self.dst = torch.empty(self.E, dtype=torch.int64, device=edges.device)
+        _lib.check(lib.tmgcn_flat_edge_ids(_p(edges), self.E, N, t_offset, _p(self.src), _p(self.dst), _stream()))
+        self._inc = None
+
+    def incidence(self):
+        if self._inc is None:
+            E, dev = self.E, self.src.device
+            keys = torch.cat([self.src, self.dst])
+            ar = torch.arange(E, device=dev, dtype=torch.int64)
+            code = torch.cat([2 * ar, 2 * ar + 1])
+            order = torch.argsort(keys, stable=True)
+            perm = code[order].contiguous()
+            row_ids, counts = torch.unique_consecutive(keys[order], return_counts=True)
+            seg = torch.zeros(row_ids.numel() + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(counts, 0, out=seg[1:])
+            self._inc = (row_ids.contiguous(), seg, perm)
+        return self._inc
+
+
+def readout_fwd_raw(y2d: torch.Tensor, plan: EdgePlan, u: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    F, Cc = y2d.shape[1], u.shape[1]
+    assert u.shape[0] == 2 * F
+    out = torch.empty(plan.E, Cc, dtype=torch.float32, device=y2d.device)
+    _lib.check(lib.tmgcn_edge_readout_fwd(_p(y2d), _p(plan.src), _p(plan.dst), _p(u), _p(out), plan.E, F, Cc,
+                                          _stream()))
+    return out
+
+
+def readout_bwd_raw(y2d, plan: EdgePlan, u, dout, need_dy=True, need_du=True):
+    lib = _lib.load()
+    F, Cc = y2d.shape[1], u.shape[1]
+    row_ids, seg, perm = plan.incidence()
+    dy = torch.empty_like(y2d) if need_dy else None
+    du = torch.empty_like(u) if need_du else None
+    ws = _ws(lib.tmgcn_edge_du_ws_bytes(F, Cc)) if need_du else None
+    _lib.check(lib.tmgcn_edge_readout_bwd(_p(y2d), _p(plan.src), _p(plan.dst), _p(u), _p(dout), _p(row_ids), _p(seg),
+                                          _p(perm), row_ids.numel(), _p(dy), _p(du), y2d.shape[0], plan.E, F, Cc,
+                                          _p(ws), _stream()))
+    return dy, du
+
+
+# --------------------------------------------------------------------------
+# autograd wiring
+# --------------------------------------------------------------------------
+class _Stencil(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, band, t0, t1, halo):
+        ctx.args = (band, t0, t1, halo)
+        return stencil_fwd(x.contiguous(), band, t0, t1, halo)
+
+    @staticmethod
+    def backward(ctx, g):
+        band, t0, t1, halo = ctx.args
+        return stencil_bwd(g.contiguous(), band, t0, t1, halo), None, None, None, None
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, csr, act):
+        y = spmm_raw(csr, x.contiguous(), act)
+        ctx.csr, ctx.act = csr, act
+        if act:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        g = g.contiguous()
+        if ctx.act:
+            (y,) = ctx.saved_tensors
+            ge = torch.empty_like(g)
+            _lib.check(lib.tmgcn_act_bwd(_p(y), _p(g), _p(ge), g.numel(), ctx.act, _stream()))
+            g = ge
+        return spmm_raw(ctx.csr.transpose(), g, 0), None, None
+
+
+class _Gemm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, w, act):
+        p, w = p.contiguous(), w.contiguous()
+        y = gemm_fwd_raw(p, w, act)
+        ctx.act = act
+        ctx.save_for_backward(p, w, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        p, w, y = ctx.saved_tensors
+        dp, dw = gemm_bwd_raw(p, w, y, g.contiguous(), ctx.act, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dp, dw, None
+
+
+class _Readout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, u, plan):
+        y2d = y.contiguous().reshape(-1, y.shape[-1])
+        u = u.contiguous()
+        ctx.plan, ctx.shape = plan, y.shape
+        ctx.save_for_backward(y2d, u)
+        return readout_fwd_raw(y2d, plan, u)
+
+    @staticmethod
+    def backward(ctx, g):
+        y2d, u = ctx.saved_tensors
+        dy, du = readout_bwd_raw(y2d, ctx.plan, u, g.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return (dy.reshape(ctx.shape) if dy is not None else None), du, None
+
+
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, plan):
+        lib = _lib.load()
+        F = y.shape[-1]
+        y2d = y.contiguous().reshape(-1, F)
+        z = torch.empty(plan.E, 2 * F, dtype=torch.float32, device=y.device)
+        _lib.check(lib.tmgcn_edge_gather_fwd(_p(y2d), _p(plan.src), _p(plan.dst), _p(z), plan.E, F, _stream()))
+        ctx.plan, ctx.shape = plan, y.shape
+        return z
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        F = ctx.shape[-1]
+        n_rows = 1
+        for s in ctx.shape[:-1]:
+            n_rows *= s
+        row_ids, seg, perm = ctx.plan.incidence()
+        dy = torch.empty(n_rows, F, dtype=torch.float32, device=g.device)
+        _lib.check(lib.tmgcn_edge_gather_bwd(_p(g.contiguous()), _p(row_ids), _p(seg), _p(perm), row_ids.numel(),
+                                             _p(dy), n_rows, F, _stream()))
+        return dy.reshape(ctx.shape), None
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        lib = _lib.load()
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        _lib.check(lib.tmgcn_act_fwd(_p(x), _p(y), x.numel(), act, _stream()))
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.empty_like(g)
+        _lib.check(lib.tmgcn_act_bwd(_p(y), _p(g), _p(dx), g.numel(), ctx.act, _stream()))
+        return dx, None
+
+
+def mtransform_dense(x, band: Band, t0=0, t1=None, halo=0):
+    """X~ = X x_3 M (ref: ehf:204), differentiable."""
+    return _Stencil.apply(x, band, t0, t1, halo)
+
+
+def spmm(csr: SliceCSR, x, act=None):
+    """facewise A[t] @ x[t] (ref: ehf:205-207), differentiable w.r.t. x."""
+    return _SpMM.apply(x, csr, ACT[act] if not isinstance(act, int) else act)
+
+
+def gemm_xw(p, w, act=None):
+    """act(p @ w) (ref: ehf:222 + ehf:332-335), differentiable."""
+    return _Gemm.apply(p, w, ACT[act] if not isinstance(act, int) else act)
+
+
+def edge_readout(y, u, plan: EdgePlan):
+    """[y[src] || y[dst]] @ u (ref: ehf:228-232), differentiable."""
+    return _Readout.apply(y, u, plan)
+
+
+def edge_gather(y, plan: EdgePlan):
+    """[y[src] || y[dst]] (ref: ehf:228-230), differentiable."""
+    return _Gather.apply(y, plan)
+
+
+def activation(x, act):
+    return _Act.apply(x, ACT[act] if not isinstance(act, int) else act)
