@@ -437,7 +437,7 @@ def test_module_errors(tg, golden_models):
         tg.Band(torch.ones(4, 4))
     with pytest.raises(RuntimeError):
         from tmgcn_b200 import ops
-        ops.stencil_fwd(torch.zeros(4, 8, 1).cuda(), tg.Band(oracle.create_matrix_M(4, 3)), 0, 4, 3)  # halo > b-1
+        ops.stencil_fwd(torch.zeros(7, 8, 1).cuda(), tg.Band(oracle.create_matrix_M(4, 3)), 0, 4, 3)  # halo > b-1
 
 
 # --------------------------------------------------------------------------
@@ -470,3 +470,60 @@ def test_layer_f128_vs_oracle(tg, act):
     assert relerr(Hd.grad, dH_r) <= TOL_GRAD
     assert relerr(layer.W.grad, dW_r) <= TOL_GRAD
     assert relerr(layer.U.grad, dU_r) <= TOL_GRAD
+
+
+# --------------------------------------------------------------------------
+# the workspace-planned step bench.py times == the autograd path, also when sharded
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("act", ["none", "selu"])
+def test_layer_step_matches_autograd_and_sharding(tg, act):
+    from tmgcn_b200 import ops, synth
+    from tmgcn_b200.layer_step import LayerStep
+    T, N, F, Cc, b = 10, 900, 32, 3, 4
+    idx, val = synth.synth_coo(N, T, 4000, 0.8, seed=5)
+    M = oracle.create_matrix_M(T, b)
+    band = tg.Band(M)
+    A = tg.SliceCSR.from_coo(idx, val, T, N)
+    At = ops.mtransform_sparse(A, band)
+    g = torch.Generator().manual_seed(2)
+    H = torch.rand(T, N, F, generator=g).cuda()
+    W = (torch.randn(F, F, generator=g) / F ** 0.5).cuda()
+    U = torch.randn(2 * F, Cc, generator=g).cuda()
+    E = 3000
+    edges = synth.synth_edges(At, E)
+    dOut = torch.randn(E, Cc, generator=g).cuda()
+    plan = tg.EdgePlan(edges, N)
+    layer = tg.TMGCNLayer(At, band, plan, W, U, act)
+    Hd = H.clone().requires_grad_(True)
+    out_ref = layer(Hd)
+    out_ref.backward(dOut)
+    step = LayerStep(At, band, plan, F, F, Cc, act)
+    out = step.forward(H, W, U)
+    assert torch.equal(out, out_ref.detach())
+    dH, dW, dU = step.backward(dOut, W, U)
+    assert torch.equal(dH, Hd.grad) and torch.equal(dW, layer.W.grad) and torch.equal(dU, layer.U.grad)
+    # two time shards: rank 1 owns [cut, T) with a (b-1)-slice halo
+    cut, halo = 6, b - 1
+    sel = idx[0] >= cut - halo
+    idx_hi = idx[:, sel].clone()
+    idx_hi[0] -= cut - halo
+    At_hi = ops.mtransform_sparse(tg.SliceCSR.from_coo(idx_hi, val[sel], T - cut + halo, N), band, cut, T, halo)
+    e_hi = edges[:, edges[0] >= cut]
+    plan_hi = tg.EdgePlan(e_hi, N, t_offset=cut)
+    step_hi = LayerStep(At_hi, band, plan_hi, F, F, Cc, act, cut, T, halo)
+    out_hi = step_hi.forward(H[cut - halo:].contiguous(), W, U)
+    assert relerr(out_hi, out_ref.detach()[edges[0].cpu() >= cut]) <= TOL_OUT
+    sel_e = (edges[0] >= cut)
+    dH_hi, dW_hi, dU_hi = step_hi.backward(dOut[sel_e].contiguous(), W, U)
+    e_lo = edges[:, ~sel_e]
+    sel_lo = idx[0] < cut
+    At_lo = ops.mtransform_sparse(tg.SliceCSR.from_coo(idx[:, sel_lo], val[sel_lo], cut, N), band, 0, cut, 0)
+    step_lo = LayerStep(At_lo, band, tg.EdgePlan(e_lo, N), F, F, Cc, act, 0, cut, 0)
+    step_lo.forward(H[:cut].contiguous(), W, U)
+    dH_lo, dW_lo, dU_lo = step_lo.backward(dOut[~sel_e].contiguous(), W, U)
+    total = torch.zeros_like(H)
+    total[:cut] += dH_lo
+    total[cut - halo:] += dH_hi
+    assert relerr(total, Hd.grad) <= TOL_GRAD
+    assert relerr(dW_lo + dW_hi, layer.W.grad) <= TOL_GRAD
+    assert relerr(dU_lo + dU_hi, layer.U.grad) <= TOL_GRAD

@@ -1,0 +1,136 @@
+"""Workspace-planned forward+backward of one TM-GCN layer (the unit bench.py times).
+
+Same arithmetic as `TMGCNLayer` + autograd (H -> M x_3 H -> A~_t . H~_t -> act(. W) ->
+edge readout . U, then the full backward; ref: ehf:342-344, 351-355 and autograd of
+those), but every (T, N, F) intermediate lives in one of three caller-visible work
+buffers that are reused as tensors die, so a 2M-node, 32-slice, F=128 shard
+(32.8 GB per tensor) fits one 180 GB B200:
+
+    fwd   B1 = stencil(H)         H~
+          B2 = spmm(A~, B1)       P          (B1 dead)
+          B1 = act(B2 . W)        Y
+          out = readout(B1, U)
+    bwd   dU  = Z^T dOut          (reads Y rows)
+          B3 = scatter(dOut, U)   dY         (then dY *= act'(Y) in place; Y dead)
+          dW  = B2^T . B3 ,  B1 = B3 . W^T   dP   (P, dY dead)
+          B3 = spmm(A~^T, B1)     dH~
+          B2 = stencil^T(B3)      dH  (returned as a view of B2, halo slices included)
+
+With time sharding (`halo` > 0) the caller owns H as [halo | T_own] slices and is
+responsible for the halo exchange (see sharding.py); dH then carries the `halo`
+partial slices owed to the predecessor rank in front.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib, ops
+from .ops import ACT, Band, EdgePlan, SliceCSR, _p, _stream
+
+
+class LayerStep:
+    def __init__(self, At: SliceCSR, band: Band, plan: EdgePlan, F_in: int, F_out: int, C: int, act=None,
+                 t0: int = 0, t1: Optional[int] = None, halo: int = 0):
+        self.lib = _lib.load()
+        self.At, self.AtT = At, At.transpose()
+        self.band, self.plan = band, plan
+        self.t0, self.t1, self.halo = t0, (band.T if t1 is None else t1), halo
+        self.T, self.N = At.T, At.N
+        assert self.T == self.t1 - self.t0
+        self.F_in, self.F_out, self.C = F_in, F_out, C
+        self.act = ACT[act] if not isinstance(act, int) else act
+        dev = At.rowptr.device
+        self.Fmax = max(F_in, F_out)
+        n = self.T * self.N * self.Fmax
+        self.B1 = torch.empty(n, dtype=torch.float32, device=dev)
+        self.B2 = torch.empty((self.T + halo) * self.N * self.Fmax, dtype=torch.float32, device=dev)  # also holds dH
+        self.B3 = torch.empty(n, dtype=torch.float32, device=dev)
+        self.w_f32 = band.device_weights(self.t0, self.t1, torch.float32)
+        self.out = torch.empty(plan.E, C, dtype=torch.float32, device=dev)
+        self.dW = torch.empty(F_in, F_out, dtype=torch.float32, device=dev)
+        self.dU = torch.empty(2 * F_out, C, dtype=torch.float32, device=dev)
+        self.dw_ws = ops._ws(self.lib.tmgcn_gemm_dw_ws_bytes(F_in, F_out))
+        self.du_ws = ops._ws(self.lib.tmgcn_edge_du_ws_bytes(F_out, C))
+        self.inc = plan.incidence()
+        self.hook: Optional[Callable[[str], None]] = None   # called before each stage (bench timing)
+
+    def _view(self, buf, T, F):
+        return buf[: T * self.N * F].view(T, self.N, F)
+
+    def _mark(self, name):
+        if self.hook is not None:
+            self.hook(name)
+
+    def forward(self, H: torch.Tensor, W: torch.Tensor, U: torch.Tensor) -> torch.Tensor:
+        lib, T, N, st = self.lib, self.T, self.N, _stream()
+        assert H.shape == (T + self.halo, N, self.F_in) and H.is_contiguous()
+        Ht = self._view(self.B1, T, self.F_in)
+        P = self._view(self.B2, T, self.F_in)
+        Y = self._view(self.B1, T, self.F_out)
+        self._mark("stencil_fwd")
+        _lib.check(lib.tmgcn_mtransform_dense_fwd(_p(H), _p(Ht), T, self.halo, N * self.F_in, _p(self.w_f32),
+                                                  self.band.b, st))
+        self._mark("spmm_fwd")
+        _lib.check(lib.tmgcn_spmm_fwd(_p(self.At.rowptr), _p(self.At.col), _p(self.At.val), _p(Ht), _p(P), T, N,
+                                      self.F_in, 0, st))
+        self._mark("gemm_fwd")
+        _lib.check(lib.tmgcn_gemm_xw_fwd(_p(P), _p(W), _p(Y), T * N, self.F_in, self.F_out, self.act, st))
+        self._mark("readout_fwd")
+        _lib.check(lib.tmgcn_edge_readout_fwd(_p(Y), _p(self.plan.src), _p(self.plan.dst), _p(U), _p(self.out),
+                                              self.plan.E, self.F_out, self.C, st))
+        self._mark("end")
+        return self.out
+
+    def backward(self, dOut: torch.Tensor, W: torch.Tensor, U: torch.Tensor):
+        """-> dH (halo + T, N, F_in) view of a work buffer, dW, dU."""
+        lib, T, N, st = self.lib, self.T, self.N, _stream()
+        row_ids, seg, perm = self.inc
+        P = self._view(self.B2, T, self.F_in)
+        Y = self._view(self.B1, T, self.F_out)
+        dY = self._view(self.B3, T, self.F_out)
+        dP = self._view(self.B1, T, self.F_in)
+        dHt = self._view(self.B3, T, self.F_in)
+        dH = self._view(self.B2, T + self.halo, self.F_in)
+        self._mark("readout_bwd")
+        _lib.check(lib.tmgcn_edge_readout_bwd(_p(Y), _p(self.plan.src), _p(self.plan.dst), _p(U), _p(dOut),
+                                              _p(row_ids), _p(seg), _p(perm), row_ids.numel(), _p(dY), _p(self.dU),
+                                              T * N, self.plan.E, self.F_out, self.C, _p(self.du_ws), st))
+        if self.act:
+            self._mark("act_bwd")
+            _lib.check(lib.tmgcn_act_bwd(_p(Y), _p(dY), _p(dY), dY.numel(), self.act, st))
+        self._mark("gemm_bwd")
+        _lib.check(lib.tmgcn_gemm_dw_dx_bwd(_p(P), _p(W), None, _p(dY), _p(dP), _p(self.dW), T * N, self.F_in,
+                                            self.F_out, 0, _p(self.dw_ws), st))
+        self._mark("spmm_bwd")
+        _lib.check(lib.tmgcn_spmm_fwd(_p(self.AtT.rowptr), _p(self.AtT.col), _p(self.AtT.val), _p(dP), _p(dHt), T, N,
+                                      self.F_in, 0, st))
+        self._mark("stencil_bwd")
+        _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(dHt), _p(dH), T, self.halo, N * self.F_in, _p(self.w_f32),
+                                                  self.band.b, st))
+        self._mark("end")
+        return dH, self.dW, self.dU
+
+    # ---- algorithmic bytes per stage, whole shard --------
+    def algorithmic_bytes(self, l2_bytes: int) -> dict:
+        T, N, Fi, Fo, E, C = self.T, self.N, self.F_in, self.F_out, self.plan.E, self.C
+        nnz = self.At.nnz
+        n_t = self.At.slice_nnz().double()
+
+        def spmm(F):
+            if 4 * N * F > l2_bytes:
+                gather = 4.0 * F * nnz
+            else:
+                gather = 4.0 * F * float(torch.clamp(n_t, max=N).sum())
+            return 8.0 * nnz + 4.0 * (N + 1) * T + gather + 4.0 * N * F * T
+        # classifier folded in: the (E, 2F) concat is never written (SURVEY's unfused figure adds 8*F*E)
+        edge_fwd = 16.0 * E + 8.0 * Fo * E + 4.0 * C * E
+        edge_bwd = 32.0 * E + 4.0 * C * E + 4.0 * N * Fo * T + 8.0 * Fo * E
+        return {
+            "stencil_fwd": 8.0 * N * Fi * T, "stencil_bwd": 8.0 * N * Fi * T,
+            "spmm_fwd": spmm(Fi), "spmm_bwd": spmm(Fi),
+            "gemm_fwd": 4.0 * N * (Fi + Fo) * T + 4.0 * Fi * Fo,
+            "gemm_bwd": 2 * (4.0 * N * (Fi + Fo) * T + 4.0 * Fi * Fo),
+            "readout_fwd": edge_fwd, "readout_bwd": edge_bwd,
+        }

@@ -1,0 +1,111 @@
+"""Time sharding across ranks: rank r owns a contiguous block of
+time slices; the banded M needs only a (b-1)-slice halo from the predecessor rank.
+
+  forward  : rank r sends its last b-1 INPUT slices to rank r+1 (dense H every step,
+             sparse A once per dataset);
+  backward : rank r sends the b-1 partial dH slices it computed for its predecessor's
+             block back to rank r-1, which adds them; dW / dU are all-reduced.
+
+One process per GPU, `torch.distributed` point-to-point + all-reduce (NCCL on the
+GPUs, gloo in the CPU tests).  No wrap-around: rank 0 has a truncated window.
+The functions are device-agnostic (they only slice, send, receive and add).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .ops import SliceCSR
+
+
+def shard_bounds(T: int, world: int, rank: int):
+    """Contiguous block [t0, t1) of rank `rank`; blocks differ by at most one slice."""
+    base, rem = divmod(T, world)
+    t0 = rank * base + min(rank, rem)
+    return t0, t0 + base + (1 if rank < rem else 0)
+
+
+def _chain(send: Optional[torch.Tensor], dst: int, recv: Optional[torch.Tensor], src: int):
+    ops = []
+    if send is not None:
+        ops.append(dist.P2POp(dist.isend, send, dst))
+    if recv is not None:
+        ops.append(dist.P2POp(dist.irecv, recv, src))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def exchange_sparse_halo(A_own: SliceCSR, halo_out: int, rank: int, world: int) -> SliceCSR:
+    """Return [last `halo_out` slices of rank-1's block | own slices] as one CSR-of-slices
+    (rank 0: own slices unchanged).  Done once per dataset, before the sparse M-transform."""
+    T, N = A_own.T, A_own.N
+    h = min(halo_out, T)
+    dev = A_own.rowptr.device
+    send_meta = recv_meta = None
+    if rank < world - 1:
+        r0 = (T - h) * N
+        base = A_own.rowptr[r0]
+        s_rowptr = (A_own.rowptr[r0:] - base).contiguous()
+        lo = int(base.item())
+        s_col = A_own.col[lo:].contiguous()
+        s_val = A_own.val[lo:].contiguous()
+        send_meta = torch.tensor([s_col.numel()], dtype=torch.int64, device=dev)
+    if rank > 0:
+        recv_meta = torch.zeros(1, dtype=torch.int64, device=dev)
+    _chain(send_meta, rank + 1, recv_meta, rank - 1)
+    r_rowptr = r_col = r_val = None
+    if rank > 0:
+        n = int(recv_meta.item())
+        r_rowptr = torch.empty(h * N + 1, dtype=torch.int64, device=dev)
+        r_col = torch.empty(n, dtype=torch.int32, device=dev)
+        r_val = torch.empty(n, dtype=A_own.val.dtype, device=dev)
+    for s, r in ((s_rowptr if rank < world - 1 else None, r_rowptr), (s_col if rank < world - 1 else None, r_col),
+                 (s_val if rank < world - 1 else None, r_val)):
+        _chain(s, rank + 1, r, rank - 1)
+    if rank == 0:
+        return A_own
+    rowptr = torch.cat([r_rowptr[:-1], A_own.rowptr + r_rowptr[-1]])
+    return SliceCSR(T + h, N, rowptr, torch.cat([r_col, A_own.col]), torch.cat([r_val, A_own.val]))
+
+
+class DenseHalo:
+    """Per-step halo exchange of the dense layer input / its gradient."""
+
+    def __init__(self, NF: int, h: int, rank: int, world: int):
+        self.NF, self.h, self.rank, self.world = NF, h, rank, world
+
+    def forward(self, H: torch.Tensor, T_own: int, halo: int):
+        """H = [halo | T_own] slices.  Fill H[:halo] from the predecessor's last slices."""
+        h = min(self.h, T_own)
+        send = H[halo + T_own - h:] if self.rank < self.world - 1 else None
+        recv = H[:halo] if self.rank > 0 and halo > 0 else None
+        _chain(send, self.rank + 1, recv, self.rank - 1)
+
+    def backward(self, dH: torch.Tensor, T_own: int, halo: int, scratch: Optional[torch.Tensor] = None):
+        """dH = [halo | T_own] slices.  Ship dH[:halo] to the predecessor, add what the
+        successor computed for our last slices."""
+        h = min(self.h, T_own)
+        send = dH[:halo] if self.rank > 0 and halo > 0 else None
+        recv = None
+        if self.rank < self.world - 1:
+            n = h * dH[0].numel()
+            recv = (scratch.reshape(-1)[:n] if scratch is not None else
+                    torch.empty(n, dtype=dH.dtype, device=dH.device)).view((h,) + tuple(dH.shape[1:]))
+        _chain(send, self.rank - 1, recv, self.rank + 1)
+        if recv is not None:
+            dH[halo + T_own - h:].add_(recv)
+
+
+def allreduce_grads(grads: List[torch.Tensor]):
+    """Sum the shared-parameter gradients (dW, dU) over ranks."""
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
