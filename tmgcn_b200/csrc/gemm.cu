@@ -56,8 +56,9 @@ int tmgcn_gemm_dw_dx_bwd(const float *p, const float *w, const float *y, const f
     TMGCN_REQUIRE(w && dy, "gemm_bwd: null pointer");
     if (dp) {
         int rc;
-        if (tc_enabled() && gemm_tc_eligible(R, Nf, K))
-            rc = gemm_tc_fwd(dy, w, dp, R, Nf, K, act, true, act == TMGCN_ACT_NONE ? nullptr : y, st);
+        // the tensor-core kernel has no fused act'(y): callers wanting it pre-apply tmgcn_act_bwd (in place)
+        if (tc_enabled() && act == TMGCN_ACT_NONE && gemm_tc_eligible(R, Nf, K))
+            rc = gemm_tc_fwd(dy, w, dp, R, Nf, K, TMGCN_ACT_NONE, true, nullptr, st);
         else
             rc = gemm_simt_dp(w, y, dy, dp, R, K, Nf, act, st);
         if (rc) return rc;

@@ -358,7 +358,14 @@ class _Gemm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         p, w, y = ctx.saved_tensors
-        dp, dw = gemm_bwd_raw(p, w, y, g.contiguous(), ctx.act, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        g = g.contiguous()
+        act = ctx.act
+        if act:   # dY <- dY * act'(Y) once, so dP can take the tensor-core path
+            lib = _lib.load()
+            ge = torch.empty_like(g)
+            _lib.check(lib.tmgcn_act_bwd(_p(y), _p(g), _p(ge), g.numel(), act, _stream()))
+            g, act = ge, 0
+        dp, dw = gemm_bwd_raw(p, w, None, g, act, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dp, dw, None
 
 
