@@ -128,18 +128,19 @@ int tmgcn_edge_gather_fwd(const float *y, const int64_t *src, const int64_t *dst
                           void *stream);
 int tmgcn_edge_readout_fwd(const float *y, const int64_t *src, const int64_t *dst, const float *u, float *out,
                            int64_t E, int F, int C, void *stream);
-/* backward.  The incidence plan makes the scatter-add deterministic: perm[2E] lists
- * (e*2+half) grouped by touched row, row_ids[R_touched], seg_ptr[R_touched+1].
+/* backward.  The incidence CSR makes the scatter-add deterministic (no atomics):
+ * inc_ptr[n_rows+1] over ALL T*N rows and perm[2E] = (e*2+half) grouped by endpoint row
+ * (built once per edge set: stable sort of the 2E endpoint ids + tmgcn_rowptr_from_sorted_rows).
  * gather_bwd : dy[row, :] = sum over incident (e, half) of dz[e, half*F:(half+1)*F]
  * readout_bwd: dy[row, :] = sum dout[e, :] . u[half*F:(half+1)*F, :]^T ;  du = z^T . dout
- * dy (n_rows, F) is fully written (rows no edge touches become 0). */
-int tmgcn_edge_gather_bwd(const float *dz, const int64_t *row_ids, const int64_t *seg_ptr, const int64_t *perm,
-                          int64_t n_touched, float *dy, int64_t n_rows, int F, void *stream);
+ * dy (n_rows, F) is written exactly once, rows no edge touches become 0.  dy or du may be
+ * NULL to skip that output.  du_ws: tmgcn_edge_du_ws_bytes(F, C) bytes of scratch. */
+int tmgcn_edge_gather_bwd(const float *dz, const int64_t *inc_ptr, const int64_t *perm, float *dy, int64_t n_rows,
+                          int F, void *stream);
 size_t tmgcn_edge_du_ws_bytes(int F, int C);
-int tmgcn_edge_readout_bwd(const float *y, const int64_t *src, const int64_t *dst, const float *u,
-                           const float *dout, const int64_t *row_ids, const int64_t *seg_ptr, const int64_t *perm,
-                           int64_t n_touched, float *dy, float *du, int64_t n_rows, int64_t E, int F, int C,
-                           void *du_ws, void *stream);
+int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
+                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *du_ws,
+                           void *stream);
 
 /* ---- elementwise activation (layer boundary, ref: ehf:332-335) ----------- */
 int tmgcn_act_fwd(const float *x, float *y, int64_t n, int act, void *stream);

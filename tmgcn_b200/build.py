@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtmgcn_b200.so")
-SOURCES = ["api.cu", "sparse.cu", "stencil.cu", "spmm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm.cu", "edge.cu"]
+SOURCES = ["api.cu", "sparse.cu", "stencil.cu", "spmm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_dw_tc.cu", "gemm.cu",
+           "edge.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
@@ -47,9 +48,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         s = os.path.join(CSRC, src)
+        headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+        headers.append(os.path.join(HERE, "..", "include", "tmgcn.h"))
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(s)
-                and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "common.cuh"))
-                and os.path.getmtime(obj) > os.path.getmtime(os.path.join(HERE, "..", "include", "tmgcn.h"))):
+                and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in headers)):
             procs.append((src, obj, None))
             continue
         cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])

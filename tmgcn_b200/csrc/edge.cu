@@ -4,11 +4,15 @@
 // classifier ehf:232 / 355 / 495; backward = autograd index_put_(accumulate)
 // (SURVEY.md section 8a rows a9-a11).
 //
-// HBM-bound row gathers: a group of G lanes (G*VEC >= F) moves one 4*F-byte
-// endpoint row with vector loads.  The classifier (2F x C, C <= 8) is folded in
-// so the (E, 2F) concat never round-trips HBM; the backward scatter-add is made
-// deterministic by an incidence list (edges grouped by touched row, built once
-// per edge set) instead of atomics.
+// HBM-bound row gathers.  The classifier (2F x C, C <= 8) is folded in so the (E, 2F)
+// concat never round-trips HBM.  The backward scatter-add is made deterministic by an
+// incidence CSR over ALL T*N rows (inc_ptr[n_rows+1], perm[2E] = e*2+half grouped by
+// endpoint row, built once per edge set) instead of atomics, and it is a single pass:
+//   S_h[row, c] = sum over incident (e, h) of dOut[e, c]            (tiny, per row)
+//   dY[row, f]  = sum_h sum_c S_h[row, c] * U[hF + f, c]            (written once, zeros included)
+//   dU[hF+f, c] = sum_rows Y[row, f] * S_h[row, c]                  (register partials per warp,
+//                                                                    block partials, fixed-order sum)
+// so Y is read once per touched row (not once per edge) and dY is written exactly once.
 #include "common.cuh"
 
 namespace tmgcn {
@@ -45,7 +49,7 @@ __global__ void gather_fwd_kernel(const float *__restrict__ y, const int64_t *__
 
 // out[e, c] = sum_f y[src[e], f] * u[f, c] + y[dst[e], f] * u[F + f, c]
 // one warp per edge; u staged in shared memory transposed as us[c][2F]
-template <int C>
+template <int C, int VEC>
 __global__ void __launch_bounds__(256) readout_fwd_kernel(const float *__restrict__ y, const int64_t *__restrict__ src,
                                                           const int64_t *__restrict__ dst, const float *__restrict__ u,
                                                           float *__restrict__ out, int64_t E, int F) {
@@ -63,10 +67,23 @@ __global__ void __launch_bounds__(256) readout_fwd_kernel(const float *__restric
         float acc[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 0.f;
-        for (int f = lane; f < 2 * F; f += 32) {
-            const float v = f < F ? __ldg(ys + f) : __ldg(yd + f - F);
+        if (VEC == 4) {
+            const int Fv = F >> 2;
+            for (int f4 = lane; f4 < 2 * Fv; f4 += 32) {
+                const float4 v = f4 < Fv ? __ldg(reinterpret_cast<const float4 *>(ys) + f4)
+                                         : __ldg(reinterpret_cast<const float4 *>(yd) + f4 - Fv);
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = fmaf(v, us[c * 2 * F + f], acc[c]);
+                for (int c = 0; c < C; ++c) {
+                    const float4 w = *reinterpret_cast<const float4 *>(us + c * 2 * F + 4 * f4);
+                    acc[c] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[c]))));
+                }
+            }
+        } else {
+            for (int f = lane; f < 2 * F; f += 32) {
+                const float v = f < F ? __ldg(ys + f) : __ldg(yd + f - F);
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = fmaf(v, us[c * 2 * F + f], acc[c]);
+            }
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -80,63 +97,129 @@ __global__ void __launch_bounds__(256) readout_fwd_kernel(const float *__restric
     }
 }
 
-// dy[row, f] = sum over incident (e, half): dz[e, half*F + f]      (CLASSIFY = false)
-//            = sum over incident (e, half): sum_c dout[e, c] * u[half*F + f, c]   (CLASSIFY = true)
-// one warp per touched row, incidences visited in list order (deterministic).
-template <bool CLASSIFY>
-__global__ void __launch_bounds__(256) scatter_rows_kernel(const float *__restrict__ g, const float *__restrict__ u,
-                                                           const int64_t *__restrict__ row_ids,
-                                                           const int64_t *__restrict__ seg_ptr,
-                                                           const int64_t *__restrict__ perm, int64_t n_touched,
-                                                           float *__restrict__ dy, int F, int C) {
-    extern __shared__ float us[];  // [2F][C] as given
-    if (CLASSIFY) {
-        for (int i = threadIdx.x; i < 2 * F * C; i += blockDim.x) us[i] = u[i];
-        __syncthreads();
-    }
+// dy[row, f] = sum over incident (e, half): dz[e, half*F + f]; every row written (zeros included)
+__global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict__ dz,
+                                                         const int64_t *__restrict__ inc_ptr,
+                                                         const int64_t *__restrict__ perm, int64_t n_rows,
+                                                         float *__restrict__ dy, int F) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t k = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); k < n_touched; k += warps_total) {
-        const int64_t row = row_ids[k];
-        const int64_t s = seg_ptr[k], e = seg_ptr[k + 1];
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
+        const int64_t s = inc_ptr[row], e = inc_ptr[row + 1];
         for (int f = lane; f < F; f += 32) {
             float acc = 0.f;
             for (int64_t q = s; q < e; ++q) {
                 const int64_t code = perm[q];
-                const int64_t edge = code >> 1;
-                const int half = (int)(code & 1);
-                if (CLASSIFY) {
-                    const float *d = g + edge * C;
-                    const float *uu = us + (half * F + f) * C;
-                    float t = 0.f;
-                    for (int c = 0; c < C; ++c) t = fmaf(__ldg(d + c), uu[c], t);
-                    acc += t;
-                } else {
-                    acc += __ldg(g + edge * 2 * F + half * F + f);
-                }
+                acc += __ldg(dz + (code >> 1) * 2 * F + (code & 1) * F + f);
             }
             dy[row * F + f] = acc;
         }
     }
 }
 
-// du partial: block b handles edges [b*chunk, (b+1)*chunk); thread owns entries of (2F x C)
-__global__ void __launch_bounds__(256) du_partial_kernel(const float *__restrict__ y, const int64_t *__restrict__ src,
-                                                         const int64_t *__restrict__ dst,
-                                                         const float *__restrict__ dout, float *__restrict__ partial,
-                                                         int64_t E, int F, int C, int64_t chunk) {
-    const int64_t e0 = (int64_t)blockIdx.x * chunk;
-    const int64_t e1 = min(E, e0 + chunk);
-    const int total = 2 * F * C;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int f2 = i / C, c = i % C;
-        const int half = f2 >= F, f = f2 - half * F;
-        float acc = 0.f;
-        for (int64_t e = e0; e < e1; ++e) {
-            const int64_t row = half ? dst[e] : src[e];
-            acc = fmaf(__ldg(y + row * F + f), __ldg(dout + e * C + c), acc);
+// fused classifier backward, see the header comment.  Lane owns features f = VEC*(lane + 32 k) .. +VEC, k < NCH.
+template <int VEC, int NCH, int CM>
+__global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restrict__ y, const float *__restrict__ u,
+                                                          const float *__restrict__ dout,
+                                                          const int64_t *__restrict__ inc_ptr,
+                                                          const int64_t *__restrict__ perm, int64_t n_rows,
+                                                          float *__restrict__ dy, float *__restrict__ du_partial,
+                                                          int F, int C) {
+    extern __shared__ float sm[];          // us[2F*C] then block reduction scratch red[8 warps][2F*C]
+    float *us = sm;
+    float *red = sm + 2 * F * C;
+    for (int i = threadIdx.x; i < 2 * F * C; i += blockDim.x) us[i] = u[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float acc[2][NCH][VEC][CM];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int c = 0; c < CM; ++c) acc[h][k][v][c] = 0.f;
+
+    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
+        const int64_t s = inc_ptr[row], e = inc_ptr[row + 1];
+        float S[2][CM];
+#pragma unroll
+        for (int c = 0; c < CM; ++c) S[0][c] = S[1][c] = 0.f;
+        for (int64_t q = s; q < e; ++q) {          // uniform loads: every lane walks the (short) list
+            const int64_t code = perm[q];
+            const float *d = dout + (code >> 1) * C;
+            const int h = (int)(code & 1);
+#pragma unroll
+            for (int c = 0; c < CM; ++c)
+                if (c < C) {
+                    const float v = __ldg(d + c);
+                    if (h) S[1][c] += v; else S[0][c] += v;
+                }
         }
-        partial[(int64_t)blockIdx.x * total + i] = acc;
+        const bool touched = e > s;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            const int f0 = VEC * (lane + 32 * k);
+            if (f0 < F) {
+                float o[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) o[v] = 0.f;
+                if (touched) {
+                    float yv[VEC];
+                    if (du_partial) {
+                        if (VEC == 4) {
+                            const float4 t4 = __ldg(reinterpret_cast<const float4 *>(y + row * F + f0));
+                            yv[0] = t4.x; yv[1 % VEC] = t4.y; yv[2 % VEC] = t4.z; yv[3 % VEC] = t4.w;
+                        } else {
+                            yv[0] = __ldg(y + row * F + f0);
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+                        for (int c = 0; c < CM; ++c)
+                            if (c < C) {
+                                o[v] = fmaf(S[0][c], us[(f0 + v) * C + c], o[v]);
+                                o[v] = fmaf(S[1][c], us[(F + f0 + v) * C + c], o[v]);
+                                if (du_partial) {
+                                    acc[0][k][v][c] = fmaf(yv[v], S[0][c], acc[0][k][v][c]);
+                                    acc[1][k][v][c] = fmaf(yv[v], S[1][c], acc[1][k][v][c]);
+                                }
+                            }
+                    }
+                }
+                if (dy) {
+                    if (VEC == 4)
+                        *reinterpret_cast<float4 *>(dy + row * F + f0) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+                    else
+                        dy[row * F + f0] = o[0];
+                }
+            }
+        }
+    }
+    if (!du_partial) return;
+    // block reduction in fixed warp order, then one partial per block
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int f = VEC * (lane + 32 * k) + v;
+                if (f < F) {
+#pragma unroll
+                    for (int c = 0; c < CM; ++c)
+                        if (c < C) red[warp * 2 * F * C + (h * F + f) * C + c] = acc[h][k][v][c];
+                }
+            }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 2 * F * C; i += blockDim.x) {
+        float sum = 0.f;
+        for (int w = 0; w < nw; ++w) sum += red[w * 2 * F * C + i];
+        du_partial[(int64_t)blockIdx.x * 2 * F * C + i] = sum;
     }
 }
 
@@ -149,11 +232,11 @@ __global__ void reduce_partials_edge(const float *__restrict__ partial, float *_
     out[i] = s;
 }
 
-static int du_chunks() { return sm_count() * 4; }
+static int du_blocks() { return sm_count() * 4; }
 
-static int warp_grid(int64_t n_warps) {
+static int warp_grid(int64_t n_warps, int cap_mult = 32) {
     int64_t blocks = ceil_div(n_warps, 8);
-    const int64_t cap = (int64_t)sm_count() * 32;
+    const int64_t cap = (int64_t)sm_count() * cap_mult;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
@@ -200,9 +283,13 @@ int tmgcn_edge_readout_fwd(const float *y, const int64_t *src, const int64_t *ds
     TMGCN_REQUIRE(smem <= 48 * 1024, "edge_readout_fwd: 2*F*C too large");
     const int grid = warp_grid(E);
     cudaStream_t st = (cudaStream_t)stream;
-#define TMGCN_RC(CC)                                                                   \
-    case CC:                                                                           \
-        readout_fwd_kernel<CC><<<grid, 256, smem, st>>>(y, src, dst, u, out, E, F);    \
+    const bool v4 = F % 4 == 0 && (uintptr_t)y % 16 == 0;
+#define TMGCN_RC(CC)                                                                       \
+    case CC:                                                                               \
+        if (v4)                                                                            \
+            readout_fwd_kernel<CC, 4><<<grid, 256, smem, st>>>(y, src, dst, u, out, E, F); \
+        else                                                                               \
+            readout_fwd_kernel<CC, 1><<<grid, 256, smem, st>>>(y, src, dst, u, out, E, F); \
         break;
     switch (C) {
         TMGCN_RC(1) TMGCN_RC(2) TMGCN_RC(3) TMGCN_RC(4) TMGCN_RC(5) TMGCN_RC(6) TMGCN_RC(7) TMGCN_RC(8)
@@ -211,52 +298,60 @@ int tmgcn_edge_readout_fwd(const float *y, const int64_t *src, const int64_t *ds
     return after_launch("readout_fwd");
 }
 
-int tmgcn_edge_gather_bwd(const float *dz, const int64_t *row_ids, const int64_t *seg_ptr, const int64_t *perm,
-                          int64_t n_touched, float *dy, int64_t n_rows, int F, void *stream) {
-    TMGCN_REQUIRE(n_touched >= 0 && n_rows >= 0 && F >= 1, "edge_gather_bwd: bad sizes");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (n_rows > 0) TMGCN_CUDA(cudaMemsetAsync(dy, 0, (size_t)n_rows * F * sizeof(float), st));
-    if (n_touched == 0) return 0;
-    TMGCN_REQUIRE(dz && row_ids && seg_ptr && perm && dy, "edge_gather_bwd: null pointer");
-    scatter_rows_kernel<false><<<warp_grid(n_touched), 256, 0, st>>>(dz, nullptr, row_ids, seg_ptr, perm, n_touched,
-                                                                     dy, F, 0);
-    return after_launch("scatter_rows");
+int tmgcn_edge_gather_bwd(const float *dz, const int64_t *inc_ptr, const int64_t *perm, float *dy, int64_t n_rows,
+                          int F, void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_gather_bwd: bad sizes");
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(inc_ptr && dy, "edge_gather_bwd: null pointer");
+    gather_bwd_kernel<<<warp_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(dz, inc_ptr, perm, n_rows, dy, F);
+    return after_launch("gather_bwd");
 }
 
-size_t tmgcn_edge_du_ws_bytes(int F, int C) { return (size_t)du_chunks() * 2 * F * C * sizeof(float); }
+size_t tmgcn_edge_du_ws_bytes(int F, int C) { return (size_t)du_blocks() * 2 * F * C * sizeof(float); }
 
-int tmgcn_edge_readout_bwd(const float *y, const int64_t *src, const int64_t *dst, const float *u,
-                           const float *dout, const int64_t *row_ids, const int64_t *seg_ptr, const int64_t *perm,
-                           int64_t n_touched, float *dy, float *du, int64_t n_rows, int64_t E, int F, int C,
-                           void *du_ws, void *stream) {
-    TMGCN_REQUIRE(n_touched >= 0 && n_rows >= 0 && E >= 0 && F >= 1, "edge_readout_bwd: bad sizes");
+int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
+                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *du_ws,
+                           void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_readout_bwd: bad sizes");
     TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_readout_bwd: C=%d outside [1, %d]", C, MAXC);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)2 * F * C * sizeof(float);
-    TMGCN_REQUIRE(smem <= 48 * 1024, "edge_readout_bwd: 2*F*C too large");
-    if (dy) {
-        if (n_rows > 0) TMGCN_CUDA(cudaMemsetAsync(dy, 0, (size_t)n_rows * F * sizeof(float), st));
-        if (n_touched > 0) {
-            TMGCN_REQUIRE(dout && u && row_ids && seg_ptr && perm, "edge_readout_bwd: null pointer");
-            scatter_rows_kernel<true><<<warp_grid(n_touched), 256, smem, st>>>(dout, u, row_ids, seg_ptr, perm,
-                                                                               n_touched, dy, F, C);
-            if (after_launch("scatter_rows<classify>")) return 1;
-        }
+    const int n_u = 2 * F * C;
+    if (n_rows == 0) {
+        if (du) TMGCN_CUDA(cudaMemsetAsync(du, 0, (size_t)n_u * sizeof(float), st));
+        return 0;
     }
+    TMGCN_REQUIRE(u && dout && inc_ptr && (dy || du), "edge_readout_bwd: null pointer");
+    TMGCN_REQUIRE(!du || (y && du_ws), "edge_readout_bwd: y and du_ws are required for dU");
+    const bool v4 = F % 4 == 0 && (!dy || (uintptr_t)dy % 16 == 0) && (!y || (uintptr_t)y % 16 == 0);
+    const int per_lane = v4 ? 4 : 1;
+    const int nch = (F + 32 * per_lane - 1) / (32 * per_lane);
+    TMGCN_REQUIRE(nch <= 4, "edge_readout_bwd: F=%d too large", F);
+    const size_t smem = (size_t)n_u * sizeof(float) * (du ? 9 : 1);
+    TMGCN_REQUIRE(smem <= 200 * 1024, "edge_readout_bwd: 2*F*C too large");
+    int grid = warp_grid(n_rows, 4);
+    if (grid > du_blocks()) grid = du_blocks();
+    float *partial = du ? (float *)du_ws : nullptr;
+#define TMGCN_LAUNCH(V, K, CMX)                                                                                   \
+    {                                                                                                             \
+        auto kern = readout_bwd_kernel<V, K, CMX>;                                                                \
+        if (smem > 48 * 1024)                                                                                     \
+            TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        kern<<<grid, 256, smem, st>>>(y, u, dout, inc_ptr, perm, n_rows, dy, partial, F, C);                      \
+    }
+#define TMGCN_BY_C(V, K)                                  \
+    if (C <= 2) TMGCN_LAUNCH(V, K, 2)                     \
+    else if (C <= 4) TMGCN_LAUNCH(V, K, 4)                \
+    else TMGCN_LAUNCH(V, K, 8)
+    if (v4) {
+        if (nch == 1) { TMGCN_BY_C(4, 1) } else { TMGCN_BY_C(4, 4) }
+    } else {
+        if (nch == 1) { TMGCN_BY_C(1, 1) } else { TMGCN_BY_C(1, 4) }
+    }
+#undef TMGCN_BY_C
+#undef TMGCN_LAUNCH
+    if (after_launch("readout_bwd")) return 1;
     if (du) {
-        if (E == 0) {
-            TMGCN_CUDA(cudaMemsetAsync(du, 0, smem, st));
-            return 0;
-        }
-        TMGCN_REQUIRE(y && src && dst && dout && du_ws, "edge_readout_bwd: null pointer (du)");
-        int64_t n_chunks = ceil_div(E, 64);
-        if (n_chunks > du_chunks()) n_chunks = du_chunks();
-        const int64_t chunk = ceil_div(E, n_chunks);
-        n_chunks = ceil_div(E, chunk);
-        du_partial_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(y, src, dst, dout, (float *)du_ws, E, F, C, chunk);
-        if (after_launch("du_partial")) return 1;
-        reduce_partials_edge<<<(unsigned)ceil_div(2 * F * C, 256), 256, 0, st>>>((const float *)du_ws, du,
-                                                                                 (int)n_chunks, 2 * F * C);
+        reduce_partials_edge<<<(unsigned)ceil_div(n_u, 256), 256, 0, st>>>(partial, du, grid, n_u);
         if (after_launch("reduce_partials_edge")) return 1;
     }
     return 0;

@@ -16,6 +16,8 @@ int gemm_simt_dw(const float *p, const float *y, const float *dy, float *dw, int
 bool gemm_tc_eligible(int64_t R, int K, int Nf);
 int gemm_tc_fwd(const float *a, const float *w, float *c, int64_t R, int K, int Nf, int act, bool trans_w,
                 const float *yaux, cudaStream_t st);
+bool gemm_dw_tc_eligible(int64_t R, int KI, int NO);
+int gemm_dw_tc(const float *p, const float *dy, float *dw, int64_t R, int KI, int NO, float *ws, cudaStream_t st);
 
 static bool tc_enabled() {
     static int v = -1;
@@ -65,7 +67,11 @@ int tmgcn_gemm_dw_dx_bwd(const float *p, const float *w, const float *y, const f
     }
     if (dw) {
         TMGCN_REQUIRE(p && dw_ws, "gemm_bwd: p and dw_ws are required for dW");
-        if (gemm_simt_dw(p, y, dy, dw, R, K, Nf, act, (float *)dw_ws, st)) return 1;
+        if (tc_enabled() && act == TMGCN_ACT_NONE && gemm_dw_tc_eligible(R, K, Nf)) {
+            if (gemm_dw_tc(p, dy, dw, R, K, Nf, (float *)dw_ws, st)) return 1;
+        } else if (gemm_simt_dw(p, y, dy, dw, R, K, Nf, act, (float *)dw_ws, st)) {
+            return 1;
+        }
     }
     return 0;
 }

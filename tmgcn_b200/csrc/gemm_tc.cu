@@ -26,7 +26,7 @@
 //   * warps 8-11 tcgen05.ld the accumulator, apply the activation and store rows.
 // TMEM columns: D0 [0,128) D1 [128,256) A_hi0 [256,320) A_lo0 [320,384) A_hi1 [384,448)
 // A_lo1 [448,512).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tmgcn {
 
@@ -40,92 +40,6 @@ constexpr int RAW_STAGES = 2;
 constexpr int NUM_THREADS = 384;
 
 constexpr uint32_t TMEM_D0 = 0, TMEM_D1 = 128, TMEM_A0 = 256;  // A buffers: 128 columns each (hi 64 | lo 64)
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
-            taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-    hi = to_tf32(x);
-    lo = to_tf32(x - __uint_as_float(hi));
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (version 1 = Blackwell):
-// 8-row groups 1024 B apart (SBO), rows 128 B apart, 16 B units XOR-swizzled by row%8.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
-    d |= (uint64_t)1 << 16;                        // LBO (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;              // SBO
-    d |= (uint64_t)1 << 46;                        // descriptor version
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-    return d;
-}
 
 // byte offset of element (n, k) inside a K-major SW128 operand of NO rows
 __device__ __forceinline__ uint32_t b_offset(int n, int k, int NO) {
@@ -252,8 +166,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tf32x3_kernel(const Param
                     for (int j = 0; j < KH / 8; ++j) {
                         const int k = h * KH + j * 8;
                         const uint32_t boff = (uint32_t)((k >> 5) * NO * 128 + ((k & 31) >> 3) * 32);
-                        const uint64_t b_hi = make_desc_sw128(whi + boff);
-                        const uint64_t b_lo = make_desc_sw128(wlo + boff);
+                        const uint64_t b_hi = make_desc_sw128(whi + boff, 16, 1024);
+                        const uint64_t b_lo = make_desc_sw128(wlo + boff, 16, 1024);
                         mma_tf32_ts(d_tmem, a_hi + j * 8, b_lo, idesc, (h | j) ? 1u : 0u);
                         mma_tf32_ts(d_tmem, a_lo + j * 8, b_hi, idesc, 1u);
                         mma_tf32_ts(d_tmem, a_hi + j * 8, b_hi, idesc, 1u);

@@ -53,7 +53,7 @@ class LayerStep:
         self.dU = torch.empty(2 * F_out, C, dtype=torch.float32, device=dev)
         self.dw_ws = ops._ws(self.lib.tmgcn_gemm_dw_ws_bytes(F_in, F_out))
         self.du_ws = ops._ws(self.lib.tmgcn_edge_du_ws_bytes(F_out, C))
-        self.inc = plan.incidence()
+        self.inc = plan.incidence(self.T * self.N)
         self.hook: Optional[Callable[[str], None]] = None   # called before each stage (bench timing)
 
     def _view(self, buf, T, F):
@@ -86,7 +86,7 @@ class LayerStep:
     def backward(self, dOut: torch.Tensor, W: torch.Tensor, U: torch.Tensor):
         """-> dH (halo + T, N, F_in) view of a work buffer, dW, dU."""
         lib, T, N, st = self.lib, self.T, self.N, _stream()
-        row_ids, seg, perm = self.inc
+        inc_ptr, perm = self.inc
         P = self._view(self.B2, T, self.F_in)
         Y = self._view(self.B1, T, self.F_out)
         dY = self._view(self.B3, T, self.F_out)
@@ -94,9 +94,8 @@ class LayerStep:
         dHt = self._view(self.B3, T, self.F_in)
         dH = self._view(self.B2, T + self.halo, self.F_in)
         self._mark("readout_bwd")
-        _lib.check(lib.tmgcn_edge_readout_bwd(_p(Y), _p(self.plan.src), _p(self.plan.dst), _p(U), _p(dOut),
-                                              _p(row_ids), _p(seg), _p(perm), row_ids.numel(), _p(dY), _p(self.dU),
-                                              T * N, self.plan.E, self.F_out, self.C, _p(self.du_ws), st))
+        _lib.check(lib.tmgcn_edge_readout_bwd(_p(Y), _p(U), _p(dOut), _p(inc_ptr), _p(perm), _p(dY), _p(self.dU),
+                                              T * N, self.F_out, self.C, _p(self.du_ws), st))
         if self.act:
             self._mark("act_bwd")
             _lib.check(lib.tmgcn_act_bwd(_p(Y), _p(dY), _p(dY), dY.numel(), self.act, st))
@@ -126,7 +125,9 @@ class LayerStep:
             return 8.0 * nnz + 4.0 * (N + 1) * T + gather + 4.0 * N * F * T
         # classifier folded in: the (E, 2F) concat is never written (SURVEY's unfused figure adds 8*F*E)
         edge_fwd = 16.0 * E + 8.0 * Fo * E + 4.0 * C * E
-        edge_bwd = 32.0 * E + 4.0 * C * E + 4.0 * N * Fo * T + 8.0 * Fo * E
+        # dY written once (4NF per slice), Y read once per touched row (<= 4NF), perm + dOut + inc_ptr
+        touched = min(2.0 * E, float(N) * T)
+        edge_bwd = 16.0 * E + 8.0 * C * E + 8.0 * N * T + 4.0 * N * Fo * T + 4.0 * Fo * touched
         return {
             "stencil_fwd": 8.0 * N * Fi * T, "stencil_bwd": 8.0 * N * Fi * T,
             "spmm_fwd": spmm(Fi), "spmm_bwd": spmm(Fi),

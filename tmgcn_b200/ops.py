@@ -272,19 +272,23 @@ class EdgePlan:
         _lib.check(lib.tmgcn_flat_edge_ids(_p(edges), self.E, N, t_offset, _p(self.src), _p(self.dst), _stream()))
         self._inc = None
 
-    def incidence(self):
-        if self._inc is None:
+    def incidence(self, n_rows: int):
+        """(inc_ptr[n_rows+1], perm[2E]): incident (edge, half) codes grouped by endpoint row."""
+        if self._inc is None or self._inc[0] != n_rows:
+            lib = _lib.load()
             E, dev = self.E, self.src.device
             keys = torch.cat([self.src, self.dst])
             ar = torch.arange(E, device=dev, dtype=torch.int64)
             code = torch.cat([2 * ar, 2 * ar + 1])
-            order = torch.argsort(keys, stable=True)
+            del ar
+            skeys, order = torch.sort(keys, stable=True)
+            del keys
             perm = code[order].contiguous()
-            row_ids, counts = torch.unique_consecutive(keys[order], return_counts=True)
-            seg = torch.zeros(row_ids.numel() + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(counts, 0, out=seg[1:])
-            self._inc = (row_ids.contiguous(), seg, perm)
-        return self._inc
+            del code, order
+            inc_ptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+            _lib.check(lib.tmgcn_rowptr_from_sorted_rows(_p(skeys), skeys.numel(), n_rows, _p(inc_ptr), _stream()))
+            self._inc = (n_rows, inc_ptr, perm)
+        return self._inc[1], self._inc[2]
 
 
 def readout_fwd_raw(y2d: torch.Tensor, plan: EdgePlan, u: torch.Tensor) -> torch.Tensor:
@@ -300,13 +304,13 @@ def readout_fwd_raw(y2d: torch.Tensor, plan: EdgePlan, u: torch.Tensor) -> torch
 def readout_bwd_raw(y2d, plan: EdgePlan, u, dout, need_dy=True, need_du=True):
     lib = _lib.load()
     F, Cc = y2d.shape[1], u.shape[1]
-    row_ids, seg, perm = plan.incidence()
+    inc_ptr, perm = plan.incidence(y2d.shape[0])
     dy = torch.empty_like(y2d) if need_dy else None
     du = torch.empty_like(u) if need_du else None
     ws = _ws(lib.tmgcn_edge_du_ws_bytes(F, Cc)) if need_du else None
-    _lib.check(lib.tmgcn_edge_readout_bwd(_p(y2d), _p(plan.src), _p(plan.dst), _p(u), _p(dout), _p(row_ids), _p(seg),
-                                          _p(perm), row_ids.numel(), _p(dy), _p(du), y2d.shape[0], plan.E, F, Cc,
-                                          _p(ws), _stream()))
+    if need_dy or need_du:
+        _lib.check(lib.tmgcn_edge_readout_bwd(_p(y2d), _p(u), _p(dout), _p(inc_ptr), _p(perm), _p(dy), _p(du),
+                                              y2d.shape[0], F, Cc, _p(ws), _stream()))
     return dy, du
 
 
@@ -403,10 +407,9 @@ class _Gather(torch.autograd.Function):
         n_rows = 1
         for s in ctx.shape[:-1]:
             n_rows *= s
-        row_ids, seg, perm = ctx.plan.incidence()
+        inc_ptr, perm = ctx.plan.incidence(n_rows)
         dy = torch.empty(n_rows, F, dtype=torch.float32, device=g.device)
-        _lib.check(lib.tmgcn_edge_gather_bwd(_p(g.contiguous()), _p(row_ids), _p(seg), _p(perm), row_ids.numel(),
-                                             _p(dy), n_rows, F, _stream()))
+        _lib.check(lib.tmgcn_edge_gather_bwd(_p(g.contiguous()), _p(inc_ptr), _p(perm), _p(dy), n_rows, F, _stream()))
         return dy.reshape(ctx.shape), None
 
 
