@@ -8,8 +8,9 @@
 //   A[m = ki][k = r] = P[r][ki]   -- the transpose of the row-major tile: it is produced for
 //       free by letting TMEM lane ki (= converter thread ki) read column ki of the raw
 //       tile in shared memory (conflict-free) and tcgen05.st it as a K-major TMEM operand;
-//   B[k = r][n = no] = dY[r][no]  -- N-major, split into hi/lo and stored in the canonical
-//       MN-major SWIZZLE_128B shared-memory layout by four converter warps.
+//   B[k = r][n = no] = dY[r][no]  -- converter thread n reads column n of the raw dY tile the same
+//       way and writes row n (32 k-values = one 128-byte swizzle row) of a K-major SWIZZLE_128B
+//       shared-memory operand, split into hi and lo.
 // Raw 32-row chunks of P and dY are contiguous 16 KB blocks: one TMA bulk copy each.
 // The accumulator stays in TMEM for the whole kernel; each CTA writes one partial
 // (KI x NO) and a second kernel sums the partials in fixed order (deterministic dW).
@@ -92,9 +93,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        const uint32_t idesc = make_idesc_tf32(128, NO, /*b_mn_major=*/true);
+        const uint32_t idesc = make_idesc_tf32(128, NO, /*b_mn_major=*/false);
         const uint32_t bhi0 = smem_u32(b_hi), blo0 = smem_u32(b_lo);
-        const uint32_t lbo = (DW_KC / 8) * 1024;           // distance between 32-column N atoms
         for (int64_t i = 0; i < n_my; ++i) {
             const int s = (int)(i % DW_STAGES);
             mbar_wait(&ab_full[s], (uint32_t)((i / DW_STAGES) & 1));
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
                 const uint32_t a_hi = tmem_base + DW_TMEM_A + s * 64, a_lo = a_hi + 32;
 #pragma unroll
                 for (int j = 0; j < DW_KC / 8; ++j) {
-                    const uint64_t dhi = make_desc_sw128(bhi0 + s * b_bytes + j * 1024, lbo, 1024);
-                    const uint64_t dlo = make_desc_sw128(blo0 + s * b_bytes + j * 1024, lbo, 1024);
+                    const uint64_t dhi = make_desc_sw128(bhi0 + s * b_bytes + j * 32, 16, 1024);
+                    const uint64_t dlo = make_desc_sw128(blo0 + s * b_bytes + j * 32, 16, 1024);
                     mma_tf32_ts(tmem_base + DW_TMEM_D, a_hi + j * 8, dlo, idesc, (i | j) ? 1u : 0u);
                     mma_tf32_ts(tmem_base + DW_TMEM_D, a_lo + j * 8, dhi, idesc, 1u);
                     mma_tf32_ts(tmem_base + DW_TMEM_D, a_hi + j * 8, dhi, idesc, 1u);
@@ -146,11 +146,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
             }
         }
     } else if (warp >= 8) {
-        // ================= B converters: raw dY -> hi/lo, MN-major SWIZZLE_128B =================
-        const int t = threadIdx.x - 256;                   // 0..127
-        const int units_per_row = NO / 4;                  // 16-byte units per row
-        const int total_units = DW_KC * units_per_row;
-        const uint32_t lbo = (DW_KC / 8) * 1024;
+        // ================= B converters: column n of raw dY -> row n of a K-major SWIZZLE_128B tile =====
+        // (tf32 MN-major operands would need the SW128_32B layout; transposing here keeps the layout the
+        //  forward kernel uses: row n = 32 k-values = one 128-byte swizzle row, 8-row groups 1024 B apart)
+        const int n = threadIdx.x - 256;                   // 0..127
         for (int64_t i = 0; i < n_my; ++i) {
             const int s = (int)(i % DW_STAGES);
             const uint32_t par = (uint32_t)((i / DW_STAGES) & 1);
@@ -158,21 +157,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
             const int rows = (int)min((int64_t)DW_KC, p.R - row0);
             mbar_wait(&raw_full[s], par);
             mbar_wait(&ab_empty[s], par ^ 1);
-            const float4 *src = reinterpret_cast<const float4 *>(raw_d + s * rawd_bytes);
-            uint8_t *dhi = b_hi + s * b_bytes, *dlo = b_lo + s * b_bytes;
-            for (int u = t; u < total_units; u += 128) {
-                const int r = u / units_per_row, c = u - r * units_per_row;     // row, 16-byte unit in the row
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < rows) x = src[u];
-                uint4 h, l;
-                split_tf32(x.x, h.x, l.x);
-                split_tf32(x.y, h.y, l.y);
-                split_tf32(x.z, h.z, l.z);
-                split_tf32(x.w, h.w, l.w);
-                const uint32_t off = (uint32_t)((c >> 3) * lbo + (r >> 3) * 1024 + (r & 7) * 128 +
-                                                (((c & 7) ^ (r & 7)) << 4));
-                *reinterpret_cast<uint4 *>(dhi + off) = h;
-                *reinterpret_cast<uint4 *>(dlo + off) = l;
+            if (n < NO) {
+                const float *src = reinterpret_cast<const float *>(raw_d + s * rawd_bytes) + n;
+                uint8_t *dhi = b_hi + s * b_bytes + (n >> 3) * 1024 + (n & 7) * 128;
+                uint8_t *dlo = b_lo + s * b_bytes + (n >> 3) * 1024 + (n & 7) * 128;
+#pragma unroll
+                for (int u = 0; u < DW_KC / 4; ++u) {      // 16-byte unit = 4 consecutive k (= rows)
+                    uint4 h, l;
+                    split_tf32(4 * u + 0 < rows ? src[(4 * u + 0) * NO] : 0.f, h.x, l.x);
+                    split_tf32(4 * u + 1 < rows ? src[(4 * u + 1) * NO] : 0.f, h.y, l.y);
+                    split_tf32(4 * u + 2 < rows ? src[(4 * u + 2) * NO] : 0.f, h.z, l.z);
+                    split_tf32(4 * u + 3 < rows ? src[(4 * u + 3) * NO] : 0.f, h.w, l.w);
+                    const uint32_t off = (uint32_t)((u ^ (n & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(dhi + off) = h;
+                    *reinterpret_cast<uint4 *>(dlo + off) = l;
+                }
             }
             fence_proxy_async();                           // generic-proxy stores -> visible to the MMA
             __syncwarp();
@@ -231,7 +230,7 @@ static __global__ void dw_reduce_partials(const float *__restrict__ partial, flo
 bool gemm_dw_tc_eligible(int64_t R, int KI, int NO) {
     if (R < 1) return false;
     if (KI < 16 || KI > 128 || (KI % 4) != 0) return false;          // M = 128 lanes; rows beyond KI are zero
-    if (NO < 32 || NO > 128 || (NO % 32) != 0) return false;         // whole 32-column swizzle atoms
+    if (NO < 16 || NO > 128 || (NO % 16) != 0) return false;         // UMMA N for M = 128
     return tc::dw_smem_bytes(KI, NO) <= 227 * 1024;
 }
 
