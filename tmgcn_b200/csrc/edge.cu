@@ -142,59 +142,100 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
 #pragma unroll
                 for (int c = 0; c < CM; ++c) acc[h][k][v][c] = 0.f;
 
-    for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
-        const int64_t s = inc_ptr[row], e = inc_ptr[row + 1];
-        float S[2][CM];
+    // A warp takes RB consecutive rows per iteration so the dependent chain inc_ptr -> perm -> dOut is paid
+    // once per RB rows: lanes load the RB+1 row pointers and then one incidence each (coalesced), and the
+    // per-row class sums are assembled with shuffles.
+    constexpr int RB = 8;
+    const int64_t n_blocks = (n_rows + RB - 1) / RB;
+    for (int64_t blk = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < n_blocks; blk += warps_total) {
+        const int64_t row0 = blk * RB;
+        const int64_t ipl = inc_ptr[min(row0 + (int64_t)min(lane, RB), n_rows)];
+        const int64_t s0 = __shfl_sync(0xffffffffu, ipl, 0);
+        const int64_t e0 = __shfl_sync(0xffffffffu, ipl, RB);
+        const int n_inc = (int)(e0 - s0);
+        // incidence owned by this lane (first 32 of the block; the rare longer tail is walked serially below)
+        int myh = 0;
+        float myd[CM];
 #pragma unroll
-        for (int c = 0; c < CM; ++c) S[0][c] = S[1][c] = 0.f;
-        for (int64_t q = s; q < e; ++q) {          // uniform loads: every lane walks the (short) list
-            const int64_t code = perm[q];
+        for (int c = 0; c < CM; ++c) myd[c] = 0.f;
+        if (lane < n_inc) {
+            const int64_t code = perm[s0 + lane];
+            myh = (int)(code & 1);
             const float *d = dout + (code >> 1) * C;
-            const int h = (int)(code & 1);
 #pragma unroll
             for (int c = 0; c < CM; ++c)
-                if (c < C) {
-                    const float v = __ldg(d + c);
-                    if (h) S[1][c] += v; else S[0][c] += v;
-                }
+                if (c < C) myd[c] = __ldg(d + c);
         }
-        const bool touched = e > s;
+#pragma unroll 1
+        for (int r = 0; r < RB; ++r) {
+            const int64_t row = row0 + r;
+            if (row >= n_rows) break;
+            const int lo = (int)(__shfl_sync(0xffffffffu, ipl, r) - s0);
+            const int hi = (int)(__shfl_sync(0xffffffffu, ipl, r + 1) - s0);
+            float S[2][CM];
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-            const int f0 = VEC * (lane + 32 * k);
-            if (f0 < F) {
-                float o[VEC];
+            for (int c = 0; c < CM; ++c) S[0][c] = S[1][c] = 0.f;
+            for (int j = lo; j < hi; ++j) {
+                if (j < 32) {
+                    const int h = __shfl_sync(0xffffffffu, myh, j);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) o[v] = 0.f;
-                if (touched) {
-                    float yv[VEC];
-                    if (du_partial) {
-                        if (VEC == 4) {
-                            const float4 t4 = __ldg(reinterpret_cast<const float4 *>(y + row * F + f0));
-                            yv[0] = t4.x; yv[1 % VEC] = t4.y; yv[2 % VEC] = t4.z; yv[3 % VEC] = t4.w;
-                        } else {
-                            yv[0] = __ldg(y + row * F + f0);
+                    for (int c = 0; c < CM; ++c) {
+                        const float v = __shfl_sync(0xffffffffu, myd[c], j);
+                        if (h) S[1][c] += v; else S[0][c] += v;
+                    }
+                } else {                       // hub rows: uniform loads
+                    const int64_t code = perm[s0 + j];
+                    const float *d = dout + (code >> 1) * C;
+                    const int h = (int)(code & 1);
+#pragma unroll
+                    for (int c = 0; c < CM; ++c)
+                        if (c < C) {
+                            const float v = __ldg(d + c);
+                            if (h) S[1][c] += v; else S[0][c] += v;
+                        }
+                }
+            }
+            const bool touched = hi > lo;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int f0 = VEC * (lane + 32 * k);
+                if (f0 < F) {
+                    float o[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) o[v] = 0.f;
+                    if (touched) {
+                        float yv[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) yv[v] = 0.f;
+                        if (du_partial) {
+                            if (VEC == 4) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4 *>(y + row * F + f0));
+                                yv[0] = t4.x; yv[1 % VEC] = t4.y; yv[2 % VEC] = t4.z; yv[3 % VEC] = t4.w;
+                            } else {
+                                yv[0] = __ldg(y + row * F + f0);
+                            }
+                        }
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+                            for (int c = 0; c < CM; ++c)
+                                if (c < C) {
+                                    o[v] = fmaf(S[0][c], us[(f0 + v) * C + c], o[v]);
+                                    o[v] = fmaf(S[1][c], us[(F + f0 + v) * C + c], o[v]);
+                                    if (du_partial) {
+                                        acc[0][k][v][c] = fmaf(yv[v], S[0][c], acc[0][k][v][c]);
+                                        acc[1][k][v][c] = fmaf(yv[v], S[1][c], acc[1][k][v][c]);
+                                    }
+                                }
                         }
                     }
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-#pragma unroll
-                        for (int c = 0; c < CM; ++c)
-                            if (c < C) {
-                                o[v] = fmaf(S[0][c], us[(f0 + v) * C + c], o[v]);
-                                o[v] = fmaf(S[1][c], us[(F + f0 + v) * C + c], o[v]);
-                                if (du_partial) {
-                                    acc[0][k][v][c] = fmaf(yv[v], S[0][c], acc[0][k][v][c]);
-                                    acc[1][k][v][c] = fmaf(yv[v], S[1][c], acc[1][k][v][c]);
-                                }
-                            }
+                    if (dy) {
+                        if (VEC == 4)
+                            st_stream_f4(reinterpret_cast<float4 *>(dy + row * F + f0),
+                                         make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
+                        else
+                            dy[row * F + f0] = o[0];
                     }
-                }
-                if (dy) {
-                    if (VEC == 4)
-                        *reinterpret_cast<float4 *>(dy + row * F + f0) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
-                    else
-                        dy[row * F + f0] = o[0];
                 }
             }
         }

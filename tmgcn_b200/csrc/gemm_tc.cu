@@ -23,7 +23,8 @@
 //     hi / lo K-halves into a double-buffered TMEM A operand;
 //   * warp 1 (one elected thread) issues the MMAs into a double-buffered TMEM
 //     accumulator and tcgen05.commit's the mbarriers that recycle A and publish D;
-//   * warps 8-11 tcgen05.ld the accumulator, apply the activation and store rows.
+//   * warps 8-11 tcgen05.ld the accumulator, apply the activation, transpose 32x32 blocks through a
+//     swizzled staging tile and store full 128-byte row segments.
 // TMEM columns: D0 [0,128) D1 [128,256) A_hi0 [256,320) A_lo0 [320,384) A_hi1 [384,448)
 // A_lo1 [448,512).
 #include "tc_common.cuh"
@@ -59,19 +60,6 @@ struct Params {
     int64_t n_tiles;
 };
 
-template <int ACT>
-__device__ __forceinline__ void store_row16(float *dst, const uint32_t *v) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float4 o;
-        o.x = act_apply<ACT>(__uint_as_float(v[4 * q + 0]));
-        o.y = act_apply<ACT>(__uint_as_float(v[4 * q + 1]));
-        o.z = act_apply<ACT>(__uint_as_float(v[4 * q + 2]));
-        o.w = act_apply<ACT>(__uint_as_float(v[4 * q + 3]));
-        *reinterpret_cast<float4 *>(dst + 4 * q) = o;
-    }
-}
-
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tf32x3_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms must sit on 1024-byte boundaries of the shared window
@@ -82,7 +70,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tf32x3_kernel(const Param
     uint8_t *w_hi = smem;
     uint8_t *w_lo = smem + w_bytes;
     uint8_t *raw = smem + 2 * w_bytes;                    // RAW_STAGES x RAW_STAGE_BYTES
-    uint64_t *bars = reinterpret_cast<uint64_t *>(raw + RAW_STAGES * RAW_STAGE_BYTES);
+    uint8_t *epi_stage = raw + RAW_STAGES * RAW_STAGE_BYTES;          // 4 epilogue warps x 4 KB
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_stage + 4 * 4096);
     uint64_t *raw_full = bars, *raw_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 6, *d_full = bars + 8,
              *d_empty = bars + 10;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
@@ -217,30 +206,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tf32x3_kernel(const Param
             }
         }
     } else if (warp >= 8) {
-        // ================= epilogue: TMEM D -> act -> global rows =================
+        // ================= epilogue: TMEM D -> act -> smem transpose -> coalesced global rows =========
+        // A thread owns a ROW of the accumulator (TMEM lane), so storing straight from registers would
+        // touch 32 different 128-byte lines per instruction.  Each warp instead parks a 32-row x 32-column
+        // block in its private 4 KB staging tile (16-byte units XOR-swizzled by row: conflict-free both
+        // ways) and writes it back as 4 full 128-byte row segments per instruction.
         const int q = warp & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint8_t *stage = epi_stage + q * 4096;
         int64_t it = 0;
         for (int64_t tile = first; tile < p.n_tiles; tile += stride, ++it) {
             const int acc = (int)(it & 1);
             mbar_wait(&d_full[acc], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const int64_t row = tile * TILE_M + q * 32 + lane;
-            const bool ok = row < p.R;
-            float *dst = p.c + row * NO;
+            const int64_t row_base = tile * TILE_M + q * 32;
             const uint32_t t_d = tmem_base + lane_base + (acc ? TMEM_D1 : TMEM_D0);
-            for (int c = 0; c < NO / 16; ++c) {
-                uint32_t v[16];
-                tmem_ld16(t_d + c * 16, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (ok) {
-                    switch (p.act) {
-                        case TMGCN_ACT_RELU: store_row16<TMGCN_ACT_RELU>(dst + c * 16, v); break;
-                        case TMGCN_ACT_LEAKY: store_row16<TMGCN_ACT_LEAKY>(dst + c * 16, v); break;
-                        case TMGCN_ACT_SELU: store_row16<TMGCN_ACT_SELU>(dst + c * 16, v); break;
-                        default: store_row16<TMGCN_ACT_NONE>(dst + c * 16, v); break;
+            for (int c0 = 0; c0 < NO; c0 += 32) {
+                const int units = min(32, NO - c0) >> 2;           // 16-byte units in this column block (4 or 8)
+                uint32_t v[32];
+                tmem_ld16(t_d + c0, v);
+                if (units > 4) tmem_ld16(t_d + c0 + 16, v + 16);
+                tmem_wait_ld();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (u < units) {
+                        float4 o;
+                        o.x = act_apply_rt(__uint_as_float(v[4 * u + 0]), p.act);
+                        o.y = act_apply_rt(__uint_as_float(v[4 * u + 1]), p.act);
+                        o.z = act_apply_rt(__uint_as_float(v[4 * u + 2]), p.act);
+                        o.w = act_apply_rt(__uint_as_float(v[4 * u + 3]), p.act);
+                        *reinterpret_cast<float4 *>(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
                     }
                 }
+                __syncwarp();
+                const int u = lane & 7;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3);
+                    const int64_t row = row_base + r;
+                    if (u < units && row < p.R) {
+                        const float4 o = *reinterpret_cast<const float4 *>(stage + r * 128 + ((u ^ (r & 7)) << 4));
+                        *reinterpret_cast<float4 *>(p.c + row * NO + c0 + u * 4) = o;
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -256,7 +265,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tf32x3_kernel(const Param
 }
 
 static size_t smem_bytes(int KR, int NO) {
-    return (size_t)2 * KR * NO * 4 + (size_t)RAW_STAGES * RAW_STAGE_BYTES + 16 * 8 + 1024 /* alignment slack */;
+    return (size_t)2 * KR * NO * 4 + (size_t)RAW_STAGES * RAW_STAGE_BYTES + 4 * 4096 + 16 * 8 +
+           1024 /* alignment slack */;
 }
 
 }  // namespace tc
