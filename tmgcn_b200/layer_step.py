@@ -63,18 +63,43 @@ class LayerStep:
         if self.hook is not None:
             self.hook(name)
 
-    def forward(self, H: torch.Tensor, W: torch.Tensor, U: torch.Tensor) -> torch.Tensor:
+    # ---- kernels on slice sub-ranges (pointer offsets; rowptr entries are absolute) -----------------
+    def _stencil_fwd(self, H, Ht, t_lo, t_hi):
+        """outputs [t_lo, t_hi) of this shard; inputs start `self.halo + t_lo - hh` slices into H."""
+        hh = min(self.band.b - 1, self.halo + t_lo)
+        NF = self.N * self.F_in
+        _lib.check(self.lib.tmgcn_mtransform_dense_fwd(
+            _p(H[self.halo + t_lo - hh:]), _p(Ht[t_lo:]), t_hi - t_lo, hh, NF,
+            _p(self.w_f32[t_lo:]), self.band.b, _stream()))
+
+    def _spmm(self, csr, x, y, t_lo, t_hi, F):
+        _lib.check(self.lib.tmgcn_spmm_fwd(_p(csr.rowptr[t_lo * self.N:]), _p(csr.col), _p(csr.val), _p(x[t_lo:]),
+                                           _p(y[t_lo:]), t_hi - t_lo, self.N, F, 0, _stream()))
+
+    def forward(self, H: torch.Tensor, W: torch.Tensor, U: torch.Tensor, comm=None) -> torch.Tensor:
+        """comm: a sharding.ShardComm -> the forward halo exchange runs on its stream while the slices that
+        do not depend on the halo are transformed and propagated."""
         lib, T, N, st = self.lib, self.T, self.N, _stream()
         assert H.shape == (T + self.halo, N, self.F_in) and H.is_contiguous()
         Ht = self._view(self.B1, T, self.F_in)
         P = self._view(self.B2, T, self.F_in)
         Y = self._view(self.B1, T, self.F_out)
-        self._mark("stencil_fwd")
-        _lib.check(lib.tmgcn_mtransform_dense_fwd(_p(H), _p(Ht), T, self.halo, N * self.F_in, _p(self.w_f32),
-                                                  self.band.b, st))
-        self._mark("spmm_fwd")
-        _lib.check(lib.tmgcn_spmm_fwd(_p(self.At.rowptr), _p(self.At.col), _p(self.At.val), _p(Ht), _p(P), T, N,
-                                      self.F_in, 0, st))
+        hb = min(self.band.b - 1, T) if (comm is not None and self.halo > 0) else 0
+        if comm is not None:
+            self._mark("halo_fwd_start")
+            comm.start_forward(H, T, self.halo)
+        if hb < T:
+            self._mark("stencil_fwd")
+            self._stencil_fwd(H, Ht, hb, T)
+            self._mark("spmm_fwd")
+            self._spmm(self.At, Ht, P, hb, T, self.F_in)
+        if hb > 0:
+            self._mark("halo_fwd_wait")
+            comm.wait(comm.fwd_done)
+            self._mark("stencil_fwd")
+            self._stencil_fwd(H, Ht, 0, hb)
+            self._mark("spmm_fwd")
+            self._spmm(self.At, Ht, P, 0, hb, self.F_in)
         self._mark("gemm_fwd")
         _lib.check(lib.tmgcn_gemm_xw_fwd(_p(P), _p(W), _p(Y), T * N, self.F_in, self.F_out, self.act, st))
         self._mark("readout_fwd")
@@ -83,8 +108,9 @@ class LayerStep:
         self._mark("end")
         return self.out
 
-    def backward(self, dOut: torch.Tensor, W: torch.Tensor, U: torch.Tensor):
-        """-> dH (halo + T, N, F_in) view of a work buffer, dW, dU."""
+    def backward(self, dOut: torch.Tensor, W: torch.Tensor, U: torch.Tensor, comm=None):
+        """-> dH (halo + T, N, F_in) view of a work buffer, dW, dU.  With `comm` the partial-gradient halo
+        and the dW/dU all-reduce overlap the main backward stencil; dH[halo:] is then complete."""
         lib, T, N, st = self.lib, self.T, self.N, _stream()
         inc_ptr, perm = self.inc
         P = self._view(self.B2, T, self.F_in)
@@ -93,6 +119,7 @@ class LayerStep:
         dP = self._view(self.B1, T, self.F_in)
         dHt = self._view(self.B3, T, self.F_in)
         dH = self._view(self.B2, T + self.halo, self.F_in)
+        NF = N * self.F_in
         self._mark("readout_bwd")
         _lib.check(lib.tmgcn_edge_readout_bwd(_p(Y), _p(U), _p(dOut), _p(inc_ptr), _p(perm), _p(dY), _p(self.dU),
                                               T * N, self.F_out, self.C, _p(self.du_ws), st))
@@ -102,12 +129,38 @@ class LayerStep:
         self._mark("gemm_bwd")
         _lib.check(lib.tmgcn_gemm_dw_dx_bwd(_p(P), _p(W), None, _p(dY), _p(dP), _p(self.dW), T * N, self.F_in,
                                             self.F_out, 0, _p(self.dw_ws), st))
+        if comm is not None:
+            comm.start_allreduce([self.dW, self.dU])
         self._mark("spmm_bwd")
-        _lib.check(lib.tmgcn_spmm_fwd(_p(self.AtT.rowptr), _p(self.AtT.col), _p(self.AtT.val), _p(dP), _p(dHt), T, N,
-                                      self.F_in, 0, st))
+        self._spmm(self.AtT, dP, dHt, 0, T, self.F_in)
+        recv = None
+        if comm is not None:
+            # B1 (dP) is dead now: use it as the send / receive staging for the gradient halo
+            h = min(self.band.b - 1, T)
+            need = (self.halo + 2 * h) * NF
+            buf = self.B1 if need <= self.B1.numel() else torch.empty(need, dtype=torch.float32, device=dH.device)
+            stage = buf[:need].view(self.halo + 2 * h, N, self.F_in)
+            send = None
+            if self.halo > 0:
+                # the partial sums owed to the predecessor depend only on our first h outputs
+                self._mark("stencil_bwd")
+                _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(dHt), _p(stage), h, self.halo, NF, _p(self.w_f32),
+                                                          self.band.b, st))
+                send = stage[: self.halo]
+            if comm.rank < comm.world - 1:
+                recv = stage[self.halo + h:]
+            self._mark("halo_bwd_start")
+            comm.start_backward(send, recv)
         self._mark("stencil_bwd")
-        _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(dHt), _p(dH), T, self.halo, N * self.F_in, _p(self.w_f32),
+        _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(dHt), _p(dH), T, self.halo, NF, _p(self.w_f32),
                                                   self.band.b, st))
+        if comm is not None:
+            self._mark("halo_bwd_wait")
+            comm.wait(comm.bwd_done)
+            if recv is not None:
+                self._mark("halo_bwd_add")
+                dH[self.halo + T - recv.shape[0]:].add_(recv)
+            comm.wait(comm.grads_done)
         self._mark("end")
         return dH, self.dW, self.dU
 

@@ -99,6 +99,48 @@ class DenseHalo:
             dH[halo + T_own - h:].add_(recv)
 
 
+class ShardComm:
+    """Overlapped halo exchange for `LayerStep`: the NCCL point-to-point traffic runs on its own CUDA
+    stream while the main stream works on the slices that do not need the halo.
+
+    forward : `start_forward(H)` ships our last b-1 input slices to rank+1 and receives the
+              predecessor's into H[:halo]; `main.wait_event(fwd_done)` before the first b-1 outputs.
+    backward: `start_backward(send, recv)` ships the partial dH owed to rank-1 and receives what
+              rank+1 owes us; `finish_backward(dH_tail, recv)` adds it.
+    """
+
+    def __init__(self, h: int, rank: int, world: int, device):
+        self.h, self.rank, self.world = h, rank, world
+        self.stream = torch.cuda.Stream(device=device)
+        self.fwd_done = torch.cuda.Event()
+        self.bwd_done = torch.cuda.Event()
+        self.grads_done = torch.cuda.Event()
+        self._ready = torch.cuda.Event()
+
+    def _on_comm_stream(self, fn, done_event):
+        main = torch.cuda.current_stream()
+        self._ready.record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._ready)
+            fn()
+            done_event.record(self.stream)
+
+    def start_forward(self, H: torch.Tensor, T_own: int, halo: int):
+        h = min(self.h, T_own)
+        send = H[halo + T_own - h:] if self.rank < self.world - 1 else None
+        recv = H[:halo] if self.rank > 0 and halo > 0 else None
+        self._on_comm_stream(lambda: _chain(send, self.rank + 1, recv, self.rank - 1), self.fwd_done)
+
+    def start_backward(self, send: Optional[torch.Tensor], recv: Optional[torch.Tensor]):
+        self._on_comm_stream(lambda: _chain(send, self.rank - 1, recv, self.rank + 1), self.bwd_done)
+
+    def start_allreduce(self, grads: List[torch.Tensor]):
+        self._on_comm_stream(lambda: allreduce_grads(grads), self.grads_done)
+
+    def wait(self, event):
+        torch.cuda.current_stream().wait_event(event)
+
+
 def allreduce_grads(grads: List[torch.Tensor]):
     """Sum the shared-parameter gradients (dW, dU) over ranks."""
     if not grads:
