@@ -21,6 +21,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL banners/logs go to stderr: rank 0 prints ONE JSON line
+
 import torch  # noqa: E402
 
 SEED = 20261017
@@ -301,6 +303,11 @@ def run_ours(args):
     one_step(True)
     ms_e2e, _ = timed(args.steps, True)
 
+    stages_all = None
+    if world > 1:
+        mine = {k: round(sum(v) / len(v), 3) for k, v in stage_times.items()}
+        stages_all = [None] * world
+        dist.all_gather_object(stages_all, mine)
     tot = torch.tensor([slice_edges_local, nnz_in], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot)
@@ -345,6 +352,7 @@ def run_ours(args):
             "layer_hbm_frac": layer_bytes / sec / 1e9 / peak,
             "layer_algorithmic_bytes": layer_bytes,
             "stages": per_stage,
+            "stages_ms_per_rank": stages_all,
             "mtransform_sparse": {"seconds": t_tr, "transform_edges_per_s": slice_edges_local / t_tr,
                                   "note": "rank-0 shard, plan+scan+run, timed once (cold)"},
         }

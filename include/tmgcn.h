@@ -95,6 +95,11 @@ int tmgcn_mtransform_dense_fwd(const float *x_in, float *x_out, int T_out, int h
                                const float *band_w, int b, void *stream);
 int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream);
+/* same, but only input slices s in [s_begin, s_end) of g_in are written (the others are left untouched):
+ * lets a rank produce the `halo` slices it owes its predecessor first (and put them on the wire) and the
+ * rest later, in place, without a staging copy. */
+int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
+                                     const float *band_w, int b, int s_begin, int s_end, void *stream);
 
 /* ---- (d) facewise SpMM  P_t = A~_t . X_t -----------------------------------
  * ref: the loop ehf:205-207 / ehf:309-311 and compute_AX ehf:301-305, 469-473.

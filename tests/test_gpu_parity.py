@@ -196,6 +196,19 @@ def test_stencil_fwd_bwd(tg, T, b, NF, norm):
     total[:cut] += g_lo.double().cpu()
     total[cut - halo:] += g_hi.double().cpu()        # halo part = what rank 1 owes rank 0
     assert relerr(total, ref_g) <= 2e-6
+    # ranged variant: the halo slices first, the rest later, in place -- together identical to one call
+    from tmgcn_b200 import _lib
+    lib = _lib.load()
+    Gh = G[cut:].cuda().contiguous()
+    w = band.device_weights(cut, T, torch.float32)
+    part = torch.full_like(g_hi, float("nan"))
+    hb = min(band.b - 1, T - cut)
+    _lib.check(lib.tmgcn_mtransform_dense_bwd_range(ops._p(Gh), ops._p(part), hb, halo, NF, ops._p(w), band.b, 0, halo,
+                                                    ops._stream()))
+    assert torch.equal(part[:halo], g_hi[:halo]) and bool(torch.isnan(part[halo:]).all())
+    _lib.check(lib.tmgcn_mtransform_dense_bwd_range(ops._p(Gh), ops._p(part), T - cut, halo, NF, ops._p(w), band.b, halo,
+                                                    halo + T - cut, ops._stream()))
+    assert torch.equal(part, g_hi)
 
 
 # --------------------------------------------------------------------------

@@ -65,7 +65,7 @@ __device__ __forceinline__ void load_weights(float *sw, const float *__restrict_
 template <int B, int V, bool REVERSE>
 __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ src, float *__restrict__ dst,
                                                       int T_out, int halo, int64_t n_vec,
-                                                      const float *__restrict__ band_w, int b) {
+                                                      const float *__restrict__ band_w, int b, int s_begin, int s_end) {
     using VT = typename Vec<V>::T;
     constexpr int C = STENCIL_C, R = ring_size(B);
     extern __shared__ float sw[];
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
 #pragma unroll
                             for (int i = 0; i < B; ++i)
                                 fma_v(acc, sw[(t0 + i + B) * B + i], ring[(q + k - i + 2 * R) % R]);
-                            st_v(out + (int64_t)s * n_vec, acc);
+                            if (s >= s_begin && s < s_end) st_v(out + (int64_t)s * n_vec, acc);
                         }
                     }
                 }
@@ -131,22 +131,23 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
 
 template <int B, int V, bool REVERSE>
 static int launch_stencil(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
-                          cudaStream_t st) {
+                          int s_begin, int s_end, cudaStream_t st) {
     const int64_t n_vec = NF / V;
     const size_t smem = (size_t)(T_out + 2 * B) * B * sizeof(float);
     TMGCN_REQUIRE(smem <= 200 * 1024, "mtransform_dense: T_out=%d too large for the weight table (b=%d)", T_out, b);
     auto kern = stencil_kernel<B, V, REVERSE>;
     if (smem > 48 * 1024) TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = 256;
-    kern<<<(unsigned)ceil_div(n_vec, threads), threads, smem, st>>>(src, dst, T_out, halo, n_vec, band_w, b);
+    kern<<<(unsigned)ceil_div(n_vec, threads), threads, smem, st>>>(src, dst, T_out, halo, n_vec, band_w, b, s_begin,
+                                                                    s_end);
     return after_launch(REVERSE ? "stencil_bwd" : "stencil_fwd");
 }
 
 template <int V, bool REVERSE>
 static int dispatch_b(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
-                      cudaStream_t st) {
+                      int s_begin, int s_end, cudaStream_t st) {
 #define TMGCN_CASE(BB) \
-    if (b <= BB) return launch_stencil<BB, V, REVERSE>(src, dst, T_out, halo, NF, band_w, b, st);
+    if (b <= BB) return launch_stencil<BB, V, REVERSE>(src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
     TMGCN_CASE(1)
     TMGCN_CASE(2)
     TMGCN_CASE(4)
@@ -165,7 +166,7 @@ static int dispatch_b(const float *src, float *dst, int T_out, int halo, int64_t
 
 template <bool REVERSE>
 static int stencil_entry(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
-                         void *stream) {
+                         int s_begin, int s_end, void *stream) {
     TMGCN_REQUIRE(T_out >= 0 && NF >= 0 && halo >= 0, "mtransform_dense: negative size");
     TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform_dense: band width b=%d outside [1, 32]", b);
     TMGCN_REQUIRE(halo <= b - 1, "mtransform_dense: halo=%d exceeds b-1=%d", halo, b - 1);
@@ -173,8 +174,8 @@ static int stencil_entry(const float *src, float *dst, int T_out, int halo, int6
     TMGCN_REQUIRE(src && dst && band_w, "mtransform_dense: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec4 = (NF % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-    if (vec4) return dispatch_b<4, REVERSE>(src, dst, T_out, halo, NF, band_w, b, st);
-    return dispatch_b<1, REVERSE>(src, dst, T_out, halo, NF, band_w, b, st);
+    if (vec4) return dispatch_b<4, REVERSE>(src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
+    return dispatch_b<1, REVERSE>(src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
 }
 
 }  // namespace tmgcn
@@ -182,10 +183,18 @@ static int stencil_entry(const float *src, float *dst, int T_out, int halo, int6
 extern "C" {
 int tmgcn_mtransform_dense_fwd(const float *x_in, float *x_out, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream) {
-    return tmgcn::stencil_entry<false>(x_in, x_out, T_out, halo, NF, band_w, b, stream);
+    return tmgcn::stencil_entry<false>(x_in, x_out, T_out, halo, NF, band_w, b, 0, halo + T_out, stream);
 }
 int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream) {
-    return tmgcn::stencil_entry<true>(g_out, g_in, T_out, halo, NF, band_w, b, stream);
+    return tmgcn::stencil_entry<true>(g_out, g_in, T_out, halo, NF, band_w, b, 0, halo + T_out, stream);
+}
+int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
+                                     const float *band_w, int b, int s_begin, int s_end, void *stream) {
+    if (s_begin < 0 || s_end > halo + T_out || s_begin > s_end) {
+        tmgcn::set_error("mtransform_dense_bwd_range: bad slice range [%d, %d)", s_begin, s_end);
+        return 1;
+    }
+    return tmgcn::stencil_entry<true>(g_out, g_in, T_out, halo, NF, band_w, b, s_begin, s_end, stream);
 }
 }

@@ -87,6 +87,7 @@ class LayerStep:
         hb = min(self.band.b - 1, T) if (comm is not None and self.halo > 0) else 0
         if comm is not None:
             self._mark("halo_fwd_start")
+            comm.wait_send_buffer_free()      # last step's gradient halo is sent from B2, which SpMM overwrites below
             comm.start_forward(H, T, self.halo)
         if hb < T:
             self._mark("stencil_fwd")
@@ -129,37 +130,46 @@ class LayerStep:
         self._mark("gemm_bwd")
         _lib.check(lib.tmgcn_gemm_dw_dx_bwd(_p(P), _p(W), None, _p(dY), _p(dP), _p(self.dW), T * N, self.F_in,
                                             self.F_out, 0, _p(self.dw_ws), st))
-        if comm is not None:
-            comm.start_allreduce([self.dW, self.dU])
-        self._mark("spmm_bwd")
-        self._spmm(self.AtT, dP, dHt, 0, T, self.F_in)
         recv = None
-        if comm is not None:
-            # B1 (dP) is dead now: use it as the send / receive staging for the gradient halo
+        if comm is None:
+            self._mark("spmm_bwd")
+            self._spmm(self.AtT, dP, dHt, 0, T, self.F_in)
+        else:
+            comm.start_allreduce([self.dW, self.dU])
+            # Gradient halo first: the partial sums owed to the predecessor depend only on our first h
+            # outputs, so propagate those slices, run the small transposed stencil and put the result on
+            # the wire while the remaining slices and the main stencil run.
             h = min(self.band.b - 1, T)
-            need = (self.halo + 2 * h) * NF
-            buf = self.B1 if need <= self.B1.numel() else torch.empty(need, dtype=torch.float32, device=dH.device)
-            stage = buf[:need].view(self.halo + 2 * h, N, self.F_in)
             send = None
+            self._mark("spmm_bwd")
+            self._spmm(self.AtT, dP, dHt, 0, h, self.F_in)
             if self.halo > 0:
-                # the partial sums owed to the predecessor depend only on our first h outputs
+                # P (B2) is dead since dW: the halo slices of dH are produced in place and sent from there
                 self._mark("stencil_bwd")
-                _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(dHt), _p(stage), h, self.halo, NF, _p(self.w_f32),
-                                                          self.band.b, st))
-                send = stage[: self.halo]
+                _lib.check(lib.tmgcn_mtransform_dense_bwd_range(_p(dHt), _p(dH), h, self.halo, NF, _p(self.w_f32),
+                                                                self.band.b, 0, self.halo, st))
+                send = dH[: self.halo]
+                self._mark("halo_bwd_start")
+                comm.start_backward(send, None)
+            if h < T:
+                self._mark("spmm_bwd")
+                self._spmm(self.AtT, dP, dHt, h, T, self.F_in)
             if comm.rank < comm.world - 1:
-                recv = stage[self.halo + h:]
-            self._mark("halo_bwd_start")
-            comm.start_backward(send, recv)
+                # dP (B1) is dead now: receive what the successor owes our last h slices into it
+                recv = self.B1[: h * NF].view(h, N, self.F_in)
+                self._mark("halo_bwd_start")
+                comm.start_backward(None, recv)
         self._mark("stencil_bwd")
-        _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(dHt), _p(dH), T, self.halo, NF, _p(self.w_f32),
-                                                  self.band.b, st))
+        _lib.check(lib.tmgcn_mtransform_dense_bwd_range(_p(dHt), _p(dH), T, self.halo, NF, _p(self.w_f32),
+                                                        self.band.b, self.halo if comm is not None else 0,
+                                                        self.halo + T, st))
         if comm is not None:
-            self._mark("halo_bwd_wait")
-            comm.wait(comm.bwd_done)
             if recv is not None:
+                self._mark("halo_bwd_wait")
+                comm.wait(comm.bwd_recv)
                 self._mark("halo_bwd_add")
                 dH[self.halo + T - recv.shape[0]:].add_(recv)
+            self._mark("grads_wait")
             comm.wait(comm.grads_done)
         self._mark("end")
         return dH, self.dW, self.dU

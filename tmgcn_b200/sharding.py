@@ -106,15 +106,17 @@ class ShardComm:
     forward : `start_forward(H)` ships our last b-1 input slices to rank+1 and receives the
               predecessor's into H[:halo]; `main.wait_event(fwd_done)` before the first b-1 outputs.
     backward: `start_backward(send, recv)` ships the partial dH owed to rank-1 and receives what
-              rank+1 owes us; `finish_backward(dH_tail, recv)` adds it.
+              rank+1 owes us; the caller waits on `bwd_recv` and adds it.
     """
 
     def __init__(self, h: int, rank: int, world: int, device):
         self.h, self.rank, self.world = h, rank, world
         self.stream = torch.cuda.Stream(device=device)
         self.fwd_done = torch.cuda.Event()
-        self.bwd_done = torch.cuda.Event()
+        self.bwd_sent = torch.cuda.Event()
+        self.bwd_recv = torch.cuda.Event()
         self.grads_done = torch.cuda.Event()
+        self.send_pending = False
         self._ready = torch.cuda.Event()
 
     def _on_comm_stream(self, fn, done_event):
@@ -132,7 +134,18 @@ class ShardComm:
         self._on_comm_stream(lambda: _chain(send, self.rank + 1, recv, self.rank - 1), self.fwd_done)
 
     def start_backward(self, send: Optional[torch.Tensor], recv: Optional[torch.Tensor]):
-        self._on_comm_stream(lambda: _chain(send, self.rank - 1, recv, self.rank + 1), self.bwd_done)
+        """The receive and the send complete independently: the step only needs `bwd_recv`; `bwd_sent`
+        guards the re-use of the send staging buffer (checked lazily at the next forward)."""
+        if recv is not None:
+            self._on_comm_stream(lambda: _chain(None, self.rank - 1, recv, self.rank + 1), self.bwd_recv)
+        if send is not None:
+            self._on_comm_stream(lambda: _chain(send, self.rank - 1, None, self.rank + 1), self.bwd_sent)
+            self.send_pending = True
+
+    def wait_send_buffer_free(self):
+        if self.send_pending:
+            self.wait(self.bwd_sent)
+            self.send_pending = False
 
     def start_allreduce(self, grads: List[torch.Tensor]):
         self._on_comm_stream(lambda: allreduce_grads(grads), self.grads_done)
