@@ -21,7 +21,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL banners/logs go to stderr: rank 0 prints ONE JSON line
+# stdout carries exactly ONE JSON line (rank 0): library banners (e.g. NCCL's version line) are sent to stderr
+# by pointing fd 1 at fd 2 and keeping a private handle on the real stdout for the result.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import torch  # noqa: E402
 
@@ -155,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "slice-edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def workload_name(args, T_local=None):
@@ -363,7 +366,7 @@ def run_ours(args):
             except Exception as ex:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "slice-edges/s", "cores": None, "kind": "port",
                                         "sample": f"failed: {ex}"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -42,7 +42,7 @@ __device__ __forceinline__ float ld_v(const float *p) { return __ldg(p); }
 __device__ __forceinline__ void st_v(float4 *p, const float4 &v) { st_stream_f4(p, v); }
 __device__ __forceinline__ void st_v(float *p, const float &v) { *p = v; }
 
-constexpr int STENCIL_C = 4;  // loads in flight per thread
+constexpr int STENCIL_C = 8;  // loads in flight per thread
 constexpr int ring_size(int B) { return STENCIL_C * ((B - 1 + STENCIL_C + STENCIL_C - 1) / STENCIL_C); }
 
 // Shared-memory weight table with B rows of zero padding on both sides so the
