@@ -139,12 +139,13 @@ int tmgcn_edge_readout_fwd(const float *y, const int64_t *src, const int64_t *ds
  * gather_bwd : dy[row, :] = sum over incident (e, half) of dz[e, half*F:(half+1)*F]
  * readout_bwd: dy[row, :] = sum dout[e, :] . u[half*F:(half+1)*F, :]^T ;  du = z^T . dout
  * dy (n_rows, F) is written exactly once, rows no edge touches become 0.  dy or du may be
- * NULL to skip that output.  du_ws: tmgcn_edge_du_ws_bytes(F, C) bytes of scratch. */
+ * NULL to skip that output.  ws: tmgcn_edge_readout_bwd_ws_bytes(n_rows, F, C) bytes of scratch
+ * (per-row class sums + per-CTA dU partials). */
 int tmgcn_edge_gather_bwd(const float *dz, const int64_t *inc_ptr, const int64_t *perm, float *dy, int64_t n_rows,
                           int F, void *stream);
-size_t tmgcn_edge_du_ws_bytes(int F, int C);
+size_t tmgcn_edge_readout_bwd_ws_bytes(int64_t n_rows, int F, int C);
 int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
-                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *du_ws,
+                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *ws,
                            void *stream);
 
 /* ---- elementwise activation (layer boundary, ref: ehf:332-335) ----------- */

@@ -48,7 +48,9 @@ __global__ void gather_fwd_kernel(const float *__restrict__ y, const int64_t *__
 }
 
 // out[e, c] = sum_f y[src[e], f] * u[f, c] + y[dst[e], f] * u[F + f, c]
-// one warp per edge; u staged in shared memory transposed as us[c][2F]
+// A warp takes EB edges per iteration: the 2*EB endpoint ids are fetched with one coalesced load each and the
+// 2*EB row gathers are all issued before any is consumed (EB KB in flight per warp at F = 128).
+// u staged in shared memory transposed as us[c][2F].
 template <int C, int VEC>
 __global__ void __launch_bounds__(256) readout_fwd_kernel(const float *__restrict__ y, const int64_t *__restrict__ src,
                                                           const int64_t *__restrict__ dst, const float *__restrict__ u,
@@ -61,6 +63,51 @@ __global__ void __launch_bounds__(256) readout_fwd_kernel(const float *__restric
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (VEC == 4 && F == 128) {
+        constexpr int EB = 4;
+        const int64_t n_blk = (E + EB - 1) / EB;
+        const float4 *y4 = reinterpret_cast<const float4 *>(y);
+        for (int64_t blk = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < n_blk; blk += warps_total) {
+            const int64_t e0 = blk * EB;
+            int64_t id = 0;                        // lanes 0..EB-1: src ids, lanes EB..2EB-1: dst ids
+            if (lane < 2 * EB) {
+                const int64_t e = e0 + (lane & (EB - 1));
+                if (e < E) id = lane < EB ? src[e] : dst[e];
+            }
+            float4 v[2 * EB];
+#pragma unroll
+            for (int k = 0; k < 2 * EB; ++k) {
+                const int64_t row = __shfl_sync(0xffffffffu, id, k);
+                v[k] = ld_stream_f4(y4 + row * 32 + lane);
+            }
+            float acc[EB][C];
+#pragma unroll
+            for (int k = 0; k < EB; ++k)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float4 ws = *reinterpret_cast<const float4 *>(us + c * 256 + 4 * lane);
+                    const float4 wd = *reinterpret_cast<const float4 *>(us + c * 256 + 128 + 4 * lane);
+                    const float4 a = v[k], bq = v[EB + k];
+                    acc[k][c] = a.x * ws.x + a.y * ws.y + a.z * ws.z + a.w * ws.w + bq.x * wd.x + bq.y * wd.y +
+                                bq.z * wd.z + bq.w * wd.w;
+                }
+#pragma unroll
+            for (int k = 0; k < EB; ++k)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[k][c] += __shfl_xor_sync(0xffffffffu, acc[k][c], o);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < EB; ++k)
+                    if (e0 + k < E) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) out[(e0 + k) * C + c] = acc[k][c];
+                    }
+            }
+        }
+        return;
+    }
     for (int64_t e = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < E; e += warps_total) {
         const float *ys = y + src[e] * F;
         const float *yd = y + dst[e] * F;
@@ -117,12 +164,48 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const float *__restrict
     }
 }
 
-// fused classifier backward, see the header comment.  Lane owns features f = VEC*(lane + 32 k) .. +VEC, k < NCH.
+// ---- classifier backward, two streaming passes (see the header comment) -------------------------
+// pass 1: S[row][h][c] = sum over incident (e, h) of dOut[e, c].  One THREAD per row: the dependent chain
+// inc_ptr -> perm -> dOut is hidden by tens of millions of independent threads; inc_ptr reads and S writes
+// are coalesced, only the dOut reads are scattered (2*E small gathers).
+template <int CM>
+__global__ void __launch_bounds__(256) row_class_sums_kernel(const float *__restrict__ dout,
+                                                             const int64_t *__restrict__ inc_ptr,
+                                                             const int64_t *__restrict__ perm, int64_t n_rows,
+                                                             float *__restrict__ S, int C) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int64_t s = inc_ptr[row], e = inc_ptr[row + 1];
+    float acc[2][CM];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) acc[0][c] = acc[1][c] = 0.f;
+    for (int64_t q = s; q < e; ++q) {
+        const int64_t code = perm[q];
+        const float *d = dout + (code >> 1) * C;
+        const int h = (int)(code & 1);
+#pragma unroll
+        for (int c = 0; c < CM; ++c)
+            if (c < C) {
+                const float v = __ldg(d + c);
+                if (h) acc[1][c] += v; else acc[0][c] += v;
+            }
+    }
+    float *o = S + row * 2 * C;
+#pragma unroll
+    for (int c = 0; c < CM; ++c)
+        if (c < C) {
+            o[c] = acc[0][c];
+            o[C + c] = acc[1][c];
+        }
+}
+
+// pass 2: dY[row, :] = sum_h sum_c S[row][h][c] * U[hF + :, c]  (every row written once, zeros included) and
+// dU[hF + f, c] += Y[row, f] * S[row][h][c] accumulated in registers (lane owns features VEC*(lane+32k)..).
+// A warp takes RB consecutive rows per iteration and issues all of its loads (S and the RB rows of Y) up
+// front; rows whose S is all zero (untouched, or sums that cancel) contribute nothing.
 template <int VEC, int NCH, int CM>
-__global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restrict__ y, const float *__restrict__ u,
-                                                          const float *__restrict__ dout,
-                                                          const int64_t *__restrict__ inc_ptr,
-                                                          const int64_t *__restrict__ perm, int64_t n_rows,
+__global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? 3 : 1)
+    readout_bwd_kernel(const float *__restrict__ y, const float *__restrict__ u, const float *__restrict__ S, int64_t n_rows,
                                                           float *__restrict__ dy, float *__restrict__ du_partial,
                                                           int F, int C) {
     extern __shared__ float sm[];          // us[2F*C] then block reduction scratch red[8 warps][2F*C]
@@ -142,60 +225,74 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
 #pragma unroll
                 for (int c = 0; c < CM; ++c) acc[h][k][v][c] = 0.f;
 
-    // A warp takes RB consecutive rows per iteration so the dependent chain inc_ptr -> perm -> dOut is paid
-    // once per RB rows: lanes load the RB+1 row pointers and then one incidence each (coalesced), and the
-    // per-row class sums are assembled with shuffles.
-    constexpr int RB = 8;
+    // this lane's slice of U is loop-invariant: keep it in registers (re-reading it from shared memory for
+    // every row cost an 8-way bank conflict per access and bounded the kernel at 2.2 TB/s)
+    float ur[2][NCH][VEC][CM];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int c = 0; c < CM; ++c) {
+                    const int f = VEC * (lane + 32 * k) + v;
+                    ur[h][k][v][c] = (f < F && c < C) ? us[(h * F + f) * C + c] : 0.f;
+                }
+    constexpr int RB = 4;
+    const int sc = 2 * C;                                   // S floats per row (<= 16)
     const int64_t n_blocks = (n_rows + RB - 1) / RB;
     for (int64_t blk = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < n_blocks; blk += warps_total) {
         const int64_t row0 = blk * RB;
-        const int64_t ipl = inc_ptr[min(row0 + (int64_t)min(lane, RB), n_rows)];
-        const int64_t s0 = __shfl_sync(0xffffffffu, ipl, 0);
-        const int64_t e0 = __shfl_sync(0xffffffffu, ipl, RB);
-        const int n_inc = (int)(e0 - s0);
-        // incidence owned by this lane (first 32 of the block; the rare longer tail is walked serially below)
-        int myh = 0;
-        float myd[CM];
+        // Everything this block needs is requested up front and independently: its S values (RB * 2C <= 64
+        // floats, two coalesced loads) and its RB rows of Y.  Y is read for every row -- gating the read on
+        // "S != 0" would save the ~30 % untouched rows but chain a second DRAM latency behind the S load
+        // (measured: 2.3 TB/s gated vs a plain stream).
+        const int64_t sbase = row0 * sc;
+        const int64_t slim = n_rows * sc;
+        const float s_lo = (lane < RB * sc && sbase + lane < slim) ? __ldg(S + sbase + lane) : 0.f;
+        const float s_hi = (lane + 32 < RB * sc && sbase + lane + 32 < slim) ? __ldg(S + sbase + lane + 32) : 0.f;
+        float yv[RB][NCH][VEC];
 #pragma unroll
-        for (int c = 0; c < CM; ++c) myd[c] = 0.f;
-        if (lane < n_inc) {
-            const int64_t code = perm[s0 + lane];
-            myh = (int)(code & 1);
-            const float *d = dout + (code >> 1) * C;
+        for (int r = 0; r < RB; ++r)
 #pragma unroll
-            for (int c = 0; c < CM; ++c)
-                if (c < C) myd[c] = __ldg(d + c);
+            for (int k = 0; k < NCH; ++k) {
+                const int f0 = VEC * (lane + 32 * k);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) yv[r][k][v] = 0.f;
+                if (du_partial && f0 < F && row0 + r < n_rows) {
+                    if (VEC == 4) {
+                        const float4 t4 = ld_stream_f4(reinterpret_cast<const float4 *>(y + (row0 + r) * F + f0));
+                        yv[r][k][0] = t4.x; yv[r][k][1 % VEC] = t4.y; yv[r][k][2 % VEC] = t4.z; yv[r][k][3 % VEC] = t4.w;
+                    } else {
+                        yv[r][k][0] = __ldg(y + (row0 + r) * F + f0);
+                    }
+                }
+            }
+        float Sr[RB][2][CM];
+        bool touched[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            touched[r] = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int c = 0; c < CM; ++c) {
+                    float v = 0.f;
+                    if (c < C) {
+                        const int idx = r * sc + h * C + c;
+                        const float a = __shfl_sync(0xffffffffu, s_lo, idx & 31);
+                        const float bq = __shfl_sync(0xffffffffu, s_hi, idx & 31);
+                        v = idx < 32 ? a : bq;
+                    }
+                    Sr[r][h][c] = v;
+                    touched[r] = touched[r] || (v != 0.f);
+                }
         }
-#pragma unroll 1
+#pragma unroll
         for (int r = 0; r < RB; ++r) {
             const int64_t row = row0 + r;
             if (row >= n_rows) break;
-            const int lo = (int)(__shfl_sync(0xffffffffu, ipl, r) - s0);
-            const int hi = (int)(__shfl_sync(0xffffffffu, ipl, r + 1) - s0);
-            float S[2][CM];
-#pragma unroll
-            for (int c = 0; c < CM; ++c) S[0][c] = S[1][c] = 0.f;
-            for (int j = lo; j < hi; ++j) {
-                if (j < 32) {
-                    const int h = __shfl_sync(0xffffffffu, myh, j);
-#pragma unroll
-                    for (int c = 0; c < CM; ++c) {
-                        const float v = __shfl_sync(0xffffffffu, myd[c], j);
-                        if (h) S[1][c] += v; else S[0][c] += v;
-                    }
-                } else {                       // hub rows: uniform loads
-                    const int64_t code = perm[s0 + j];
-                    const float *d = dout + (code >> 1) * C;
-                    const int h = (int)(code & 1);
-#pragma unroll
-                    for (int c = 0; c < CM; ++c)
-                        if (c < C) {
-                            const float v = __ldg(d + c);
-                            if (h) S[1][c] += v; else S[0][c] += v;
-                        }
-                }
-            }
-            const bool touched = hi > lo;
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
                 const int f0 = VEC * (lane + 32 * k);
@@ -203,28 +300,17 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
                     float o[VEC];
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) o[v] = 0.f;
-                    if (touched) {
-                        float yv[VEC];
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) yv[v] = 0.f;
-                        if (du_partial) {
-                            if (VEC == 4) {
-                                const float4 t4 = __ldg(reinterpret_cast<const float4 *>(y + row * F + f0));
-                                yv[0] = t4.x; yv[1 % VEC] = t4.y; yv[2 % VEC] = t4.z; yv[3 % VEC] = t4.w;
-                            } else {
-                                yv[0] = __ldg(y + row * F + f0);
-                            }
-                        }
+                    if (touched[r]) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
 #pragma unroll
                             for (int c = 0; c < CM; ++c)
                                 if (c < C) {
-                                    o[v] = fmaf(S[0][c], us[(f0 + v) * C + c], o[v]);
-                                    o[v] = fmaf(S[1][c], us[(F + f0 + v) * C + c], o[v]);
+                                    o[v] = fmaf(Sr[r][0][c], ur[0][k][v][c], o[v]);
+                                    o[v] = fmaf(Sr[r][1][c], ur[1][k][v][c], o[v]);
                                     if (du_partial) {
-                                        acc[0][k][v][c] = fmaf(yv[v], S[0][c], acc[0][k][v][c]);
-                                        acc[1][k][v][c] = fmaf(yv[v], S[1][c], acc[1][k][v][c]);
+                                        acc[0][k][v][c] = fmaf(yv[r][k][v], Sr[r][0][c], acc[0][k][v][c]);
+                                        acc[1][k][v][c] = fmaf(yv[r][k][v], Sr[r][1][c], acc[1][k][v][c]);
                                     }
                                 }
                         }
@@ -348,10 +434,14 @@ int tmgcn_edge_gather_bwd(const float *dz, const int64_t *inc_ptr, const int64_t
     return after_launch("gather_bwd");
 }
 
-size_t tmgcn_edge_du_ws_bytes(int F, int C) { return (size_t)du_blocks() * 2 * F * C * sizeof(float); }
+size_t tmgcn_edge_readout_bwd_ws_bytes(int64_t n_rows, int F, int C) {
+    // per-row class sums S (n_rows x 2 x C) followed by the per-CTA dU partials
+    const size_t s_bytes = ((size_t)(n_rows > 0 ? n_rows : 0) * 2 * C * sizeof(float) + 255) & ~(size_t)255;
+    return s_bytes + (size_t)du_blocks() * 2 * F * C * sizeof(float);
+}
 
 int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
-                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *du_ws,
+                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *ws,
                            void *stream) {
     TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_readout_bwd: bad sizes");
     TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_readout_bwd: C=%d outside [1, %d]", C, MAXC);
@@ -361,23 +451,39 @@ int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, co
         if (du) TMGCN_CUDA(cudaMemsetAsync(du, 0, (size_t)n_u * sizeof(float), st));
         return 0;
     }
-    TMGCN_REQUIRE(u && dout && inc_ptr && (dy || du), "edge_readout_bwd: null pointer");
-    TMGCN_REQUIRE(!du || (y && du_ws), "edge_readout_bwd: y and du_ws are required for dU");
+    TMGCN_REQUIRE(u && dout && inc_ptr && ws && (dy || du), "edge_readout_bwd: null pointer");
+    TMGCN_REQUIRE(!du || y, "edge_readout_bwd: y is required for dU");
+    float *S = (float *)ws;
+    const size_t s_bytes = ((size_t)n_rows * 2 * C * sizeof(float) + 255) & ~(size_t)255;
+    float *partial = du ? (float *)((char *)ws + s_bytes) : nullptr;
+    {   // pass 1
+        const unsigned g = (unsigned)ceil_div(n_rows, 256);
+        if (C <= 2) row_class_sums_kernel<2><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
+        else if (C <= 4) row_class_sums_kernel<4><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
+        else row_class_sums_kernel<8><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
+        if (after_launch("row_class_sums")) return 1;
+    }
     const bool v4 = F % 4 == 0 && (!dy || (uintptr_t)dy % 16 == 0) && (!y || (uintptr_t)y % 16 == 0);
     const int per_lane = v4 ? 4 : 1;
     const int nch = (F + 32 * per_lane - 1) / (32 * per_lane);
     TMGCN_REQUIRE(nch <= 4, "edge_readout_bwd: F=%d too large", F);
     const size_t smem = (size_t)n_u * sizeof(float) * (du ? 9 : 1);
     TMGCN_REQUIRE(smem <= 200 * 1024, "edge_readout_bwd: 2*F*C too large");
-    int grid = warp_grid(n_rows, 4);
-    if (grid > du_blocks()) grid = du_blocks();
-    float *partial = du ? (float *)du_ws : nullptr;
+    int grid = 0;
+    // persistent grid = exactly one wave of resident CTAs (a partial second wave would run at low occupancy)
 #define TMGCN_LAUNCH(V, K, CMX)                                                                                   \
     {                                                                                                             \
         auto kern = readout_bwd_kernel<V, K, CMX>;                                                                \
         if (smem > 48 * 1024)                                                                                     \
             TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-        kern<<<grid, 256, smem, st>>>(y, u, dout, inc_ptr, perm, n_rows, dy, partial, F, C);                      \
+        int per_sm = 1;                                                                                           \
+        TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                      \
+        if (per_sm < 1) per_sm = 1;                                                                               \
+        if (per_sm > 4) per_sm = 4;                                                                               \
+        grid = sm_count() * per_sm;                                                                               \
+        const int64_t want = ceil_div(n_rows, 8 * 4);                                                             \
+        if (grid > want) grid = (int)(want < 1 ? 1 : want);                                                       \
+        kern<<<grid, 256, smem, st>>>(y, u, S, n_rows, dy, partial, F, C);                                        \
     }
 #define TMGCN_BY_C(V, K)                                  \
     if (C <= 2) TMGCN_LAUNCH(V, K, 2)                     \

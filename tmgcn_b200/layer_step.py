@@ -52,7 +52,7 @@ class LayerStep:
         self.dW = torch.empty(F_in, F_out, dtype=torch.float32, device=dev)
         self.dU = torch.empty(2 * F_out, C, dtype=torch.float32, device=dev)
         self.dw_ws = ops._ws(self.lib.tmgcn_gemm_dw_ws_bytes(F_in, F_out))
-        self.du_ws = ops._ws(self.lib.tmgcn_edge_du_ws_bytes(F_out, C))
+        self.du_ws = ops._ws(self.lib.tmgcn_edge_readout_bwd_ws_bytes(self.T * self.N, F_out, C))
         self.inc = plan.incidence(self.T * self.N)
         self.hook: Optional[Callable[[str], None]] = None   # called before each stage (bench timing)
 

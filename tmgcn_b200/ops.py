@@ -307,7 +307,7 @@ def readout_bwd_raw(y2d, plan: EdgePlan, u, dout, need_dy=True, need_du=True):
     inc_ptr, perm = plan.incidence(y2d.shape[0])
     dy = torch.empty_like(y2d) if need_dy else None
     du = torch.empty_like(u) if need_du else None
-    ws = _ws(lib.tmgcn_edge_du_ws_bytes(F, Cc)) if need_du else None
+    ws = _ws(lib.tmgcn_edge_readout_bwd_ws_bytes(y2d.shape[0], F, Cc))
     if need_dy or need_du:
         _lib.check(lib.tmgcn_edge_readout_bwd(_p(y2d), _p(u), _p(dout), _p(inc_ptr), _p(perm), _p(dy), _p(du),
                                               y2d.shape[0], F, Cc, _p(ws), _stream()))
