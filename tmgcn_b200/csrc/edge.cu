@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) row_class_sums_kernel(const float *__rest
 // A warp takes RB consecutive rows per iteration and issues all of its loads (S and the RB rows of Y) up
 // front; rows whose S is all zero (untouched, or sums that cancel) contribute nothing.
 template <int VEC, int NCH, int CM>
-__global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? 3 : 1)
+__global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? 2 : 1)
     readout_bwd_kernel(const float *__restrict__ y, const float *__restrict__ u, const float *__restrict__ S, int64_t n_rows,
                                                           float *__restrict__ dy, float *__restrict__ du_partial,
                                                           int F, int C) {
