@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--feat", type=int, default=128)
     ap.add_argument("--classes", type=int, default=2)
     ap.add_argument("--act", default="none")
+    ap.add_argument("--bwd", default="auto", choices=["auto", "dense", "lowrank"],
+                    help="backward formulation (auto = low-rank when the layer is linear, see layer_step.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-nodes", type=int, default=100_000, help="bounded CPU sample: nodes")
     ap.add_argument("--cpu-slices", type=int, default=8)
@@ -230,7 +232,7 @@ def run_ours(args):
     edges = synth.synth_edges(At, E, seed=SEED + rank)
     plan = tg.EdgePlan(edges, N)
     del edges
-    step = LayerStep(At, band, plan, F, F, C, args.act, t0, t1, halo)
+    step = LayerStep(At, band, plan, F, F, C, args.act, t0, t1, halo, bwd_mode=args.bwd)
     torch.cuda.empty_cache()
     gen = torch.Generator(device=dev).manual_seed(SEED + 100 + rank)
     H = torch.empty(T_local + halo, N, F, device=dev)
@@ -305,6 +307,12 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     one_step(True)
     ms_e2e, _ = timed(args.steps, True)
+    ms_dense = None
+    if step.bwd_mode == "lowrank":     # for transparency also time the general (dense-gradient) backward
+        step.bwd_mode = "dense"
+        one_step(False)
+        ms_dense, _ = timed(args.steps, False)
+        step.bwd_mode = "lowrank"
 
     stages_all = None
     if world > 1:
@@ -348,6 +356,11 @@ def run_ours(args):
                             "H, A~ and the edge list stay device-resident as the reference's ctor caches them "
                             "(ehf:195-198)"},
             "gpu_launches": launches,
+            "backward": {"mode": step.bwd_mode,
+                         "note": "lowrank = exact re-association of the backward through the rank-2C factor the "
+                                 "C-class readout hands back (linear layer, act=none); dense = general path",
+                         "dense_ms_per_step": None if ms_dense is None else ms_dense / args.steps,
+                         "dense_value": None if ms_dense is None else slice_edges / (ms_dense * 1e-3 / args.steps)},
             "roofline": {"bound": "hbm", "kernel": "spmm_rows (forward SpMM, all slices in one launch)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,

@@ -144,6 +144,18 @@ int tmgcn_edge_readout_fwd(const float *y, const int64_t *src, const int64_t *ds
 int tmgcn_edge_gather_bwd(const float *dz, const int64_t *inc_ptr, const int64_t *perm, float *dy, int64_t n_rows,
                           int F, void *stream);
 size_t tmgcn_edge_readout_bwd_ws_bytes(int64_t n_rows, int F, int C);
+/* The two passes of readout_bwd, exposed separately because the per-row class sums are a rank-2C
+ * factorisation of the whole upstream gradient (dY = S . U~): when the layer between the propagation
+ * and the readout is linear, every backward stage can run on the skinny factor (see layer_step.py).
+ * class_sums  : S[row, h, c] = sum over incident (e, h) of dout[e, c]            S is (n_rows, 2, C)
+ * factor_apply: dy[row, f] = sum_{h,c} S[row,h,c] * u[hF+f, c]     (if dy)      "expand"
+ *               du[hF+f, c] = sum_rows y[row, f] * S[row,h,c]      (if du)      "reduce"
+ * ws: tmgcn_edge_factor_ws_bytes(F, C) bytes, needed only when du is requested. */
+size_t tmgcn_edge_factor_ws_bytes(int F, int C);
+int tmgcn_edge_class_sums(const float *dout, const int64_t *inc_ptr, const int64_t *perm, float *S, int64_t n_rows,
+                          int C, void *stream);
+int tmgcn_edge_factor_apply(const float *y, const float *u, const float *S, float *dy, float *du, int64_t n_rows,
+                            int F, int C, void *ws, void *stream);
 int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
                            const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *ws,
                            void *stream);

@@ -22,6 +22,9 @@ from tmgcn_b200 import ops, sharding, synth  # noqa: E402
 from tmgcn_b200.layer_step import LayerStep  # noqa: E402
 
 
+MODE_ACT = os.environ.get("TMGCN_CHECK_ACT", "relu")   # "none" exercises the low-rank backward + its skinny halo
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -54,7 +57,7 @@ def main():
     At = ops.mtransform_sparse(A_in, band, t0, t1, halo)
     esel = (edges[0] >= t0) & (edges[0] < t1)
     plan = tg.EdgePlan(edges[:, esel], N, t_offset=t0)
-    step = LayerStep(At, band, plan, F, F, C, "relu", t0, t1, halo)
+    step = LayerStep(At, band, plan, F, F, C, MODE_ACT, t0, t1, halo)
     Hl = torch.zeros(halo + Tl, N, F, device=dev)
     Hl[halo:] = H[t0:t1].to(dev)                           # the halo slices arrive over NCCL
     comm = sharding.ShardComm(b - 1, rank, world, dev)
@@ -66,7 +69,7 @@ def main():
 
     # reference: the whole tensor on one GPU
     ok = True
-    ref = LayerStep(full_At, band, tg.EdgePlan(edges, N), F, F, C, "relu")
+    ref = LayerStep(full_At, band, tg.EdgePlan(edges, N), F, F, C, MODE_ACT, bwd_mode="dense")
     out_r = ref.forward(H.to(dev), W, U).clone()
     dH_r, dW_r, dU_r = ref.backward(dOut, W, U)
 

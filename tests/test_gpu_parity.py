@@ -488,8 +488,8 @@ def test_layer_f128_vs_oracle(tg, act):
 # --------------------------------------------------------------------------
 # the workspace-planned step bench.py times == the autograd path, also when sharded
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("act", ["none", "selu"])
-def test_layer_step_matches_autograd_and_sharding(tg, act):
+@pytest.mark.parametrize("act,mode", [("none", "dense"), ("none", "lowrank"), ("selu", "auto")])
+def test_layer_step_matches_autograd_and_sharding(tg, act, mode):
     from tmgcn_b200 import ops, synth
     from tmgcn_b200.layer_step import LayerStep
     T, N, F, Cc, b = 10, 900, 32, 3, 4
@@ -510,11 +510,18 @@ def test_layer_step_matches_autograd_and_sharding(tg, act):
     Hd = H.clone().requires_grad_(True)
     out_ref = layer(Hd)
     out_ref.backward(dOut)
-    step = LayerStep(At, band, plan, F, F, Cc, act)
+    step = LayerStep(At, band, plan, F, F, Cc, act, bwd_mode=mode)
+    assert step.bwd_mode == ("dense" if act != "none" else mode)
     out = step.forward(H, W, U)
     assert torch.equal(out, out_ref.detach())
     dH, dW, dU = step.backward(dOut, W, U)
-    assert torch.equal(dH, Hd.grad) and torch.equal(dW, layer.W.grad) and torch.equal(dU, layer.U.grad)
+    if step.bwd_mode == "dense":      # same kernels as the autograd path: bit-identical
+        assert torch.equal(dH, Hd.grad) and torch.equal(dW, layer.W.grad) and torch.equal(dU, layer.U.grad)
+    else:                             # low-rank association: same gradients to rounding
+        assert relerr(dH, Hd.grad) <= TOL_GRAD and relerr(dW, layer.W.grad) <= TOL_GRAD
+        assert relerr(dU, layer.U.grad) <= TOL_GRAD
+        with pytest.raises(ValueError):
+            LayerStep(At, band, plan, F, F, Cc, "relu", bwd_mode="lowrank")
     # two time shards: rank 1 owns [cut, T) with a (b-1)-slice halo
     cut, halo = 6, b - 1
     sel = idx[0] >= cut - halo
@@ -523,7 +530,7 @@ def test_layer_step_matches_autograd_and_sharding(tg, act):
     At_hi = ops.mtransform_sparse(tg.SliceCSR.from_coo(idx_hi, val[sel], T - cut + halo, N), band, cut, T, halo)
     e_hi = edges[:, edges[0] >= cut]
     plan_hi = tg.EdgePlan(e_hi, N, t_offset=cut)
-    step_hi = LayerStep(At_hi, band, plan_hi, F, F, Cc, act, cut, T, halo)
+    step_hi = LayerStep(At_hi, band, plan_hi, F, F, Cc, act, cut, T, halo, bwd_mode=mode)
     out_hi = step_hi.forward(H[cut - halo:].contiguous(), W, U)
     assert relerr(out_hi, out_ref.detach()[edges[0].cpu() >= cut]) <= TOL_OUT
     sel_e = (edges[0] >= cut)
@@ -531,7 +538,7 @@ def test_layer_step_matches_autograd_and_sharding(tg, act):
     e_lo = edges[:, ~sel_e]
     sel_lo = idx[0] < cut
     At_lo = ops.mtransform_sparse(tg.SliceCSR.from_coo(idx[:, sel_lo], val[sel_lo], cut, N), band, 0, cut, 0)
-    step_lo = LayerStep(At_lo, band, tg.EdgePlan(e_lo, N), F, F, Cc, act, 0, cut, 0)
+    step_lo = LayerStep(At_lo, band, tg.EdgePlan(e_lo, N), F, F, Cc, act, 0, cut, 0, bwd_mode=mode)
     step_lo.forward(H[:cut].contiguous(), W, U)
     dH_lo, dW_lo, dU_lo = step_lo.backward(dOut[~sel_e].contiguous(), W, U)
     total = torch.zeros_like(H)

@@ -41,6 +41,9 @@ PROTOTYPES = {
     "tmgcn_edge_readout_fwd": (_i, [_p, _p, _p, _p, _p, _l, _i, _i, _p]),
     "tmgcn_edge_gather_bwd": (_i, [_p, _p, _p, _p, _l, _i, _p]),
     "tmgcn_edge_readout_bwd_ws_bytes": (_z, [_l, _i, _i]),
+    "tmgcn_edge_factor_ws_bytes": (_z, [_i, _i]),
+    "tmgcn_edge_class_sums": (_i, [_p, _p, _p, _p, _l, _i, _p]),
+    "tmgcn_edge_factor_apply": (_i, [_p, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
     "tmgcn_edge_readout_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
     "tmgcn_act_fwd": (_i, [_p, _p, _l, _i, _p]),
     "tmgcn_act_bwd": (_i, [_p, _p, _p, _l, _i, _p]),

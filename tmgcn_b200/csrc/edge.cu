@@ -203,8 +203,10 @@ __global__ void __launch_bounds__(256) row_class_sums_kernel(const float *__rest
 // dU[hF + f, c] += Y[row, f] * S[row][h][c] accumulated in registers (lane owns features VEC*(lane+32k)..).
 // A warp takes RB consecutive rows per iteration and issues all of its loads (S and the RB rows of Y) up
 // front; rows whose S is all zero (untouched, or sums that cancel) contribute nothing.
-template <int VEC, int NCH, int CM>
-__global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? 2 : 1)
+// HAS_DY / HAS_DU select the expand and reduce halves at compile time: the expand-only and reduce-only
+// variants (low-rank backward) need far fewer registers and run at 5-6 CTAs per SM.
+template <int VEC, int NCH, int CM, bool HAS_DY, bool HAS_DU>
+__global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? ((HAS_DY && HAS_DU) ? 2 : (HAS_DU ? 3 : 4)) : 1)
     readout_bwd_kernel(const float *__restrict__ y, const float *__restrict__ u, const float *__restrict__ S, int64_t n_rows,
                                                           float *__restrict__ dy, float *__restrict__ du_partial,
                                                           int F, int C) {
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? 2 : 1)
                 const int f0 = VEC * (lane + 32 * k);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) yv[r][k][v] = 0.f;
-                if (du_partial && f0 < F && row0 + r < n_rows) {
+                if (HAS_DU && f0 < F && row0 + r < n_rows) {
                     if (VEC == 4) {
                         const float4 t4 = ld_stream_f4(reinterpret_cast<const float4 *>(y + (row0 + r) * F + f0));
                         yv[r][k][0] = t4.x; yv[r][k][1 % VEC] = t4.y; yv[r][k][2 % VEC] = t4.z; yv[r][k][3 % VEC] = t4.w;
@@ -306,16 +308,18 @@ __global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? 2 : 1)
 #pragma unroll
                             for (int c = 0; c < CM; ++c)
                                 if (c < C) {
-                                    o[v] = fmaf(Sr[r][0][c], ur[0][k][v][c], o[v]);
-                                    o[v] = fmaf(Sr[r][1][c], ur[1][k][v][c], o[v]);
-                                    if (du_partial) {
+                                    if (HAS_DY) {
+                                        o[v] = fmaf(Sr[r][0][c], ur[0][k][v][c], o[v]);
+                                        o[v] = fmaf(Sr[r][1][c], ur[1][k][v][c], o[v]);
+                                    }
+                                    if (HAS_DU) {
                                         acc[0][k][v][c] = fmaf(yv[r][k][v], Sr[r][0][c], acc[0][k][v][c]);
                                         acc[1][k][v][c] = fmaf(yv[r][k][v], Sr[r][1][c], acc[1][k][v][c]);
                                     }
                                 }
                         }
                     }
-                    if (dy) {
+                    if (HAS_DY) {
                         if (VEC == 4)
                             st_stream_f4(reinterpret_cast<float4 *>(dy + row * F + f0),
                                          make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? 2 : 1)
             }
         }
     }
-    if (!du_partial) return;
+    if (!HAS_DU) return;
     // block reduction in fixed warp order, then one partial per block
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -434,52 +438,60 @@ int tmgcn_edge_gather_bwd(const float *dz, const int64_t *inc_ptr, const int64_t
     return after_launch("gather_bwd");
 }
 
+size_t tmgcn_edge_factor_ws_bytes(int F, int C) { return (size_t)du_blocks() * 2 * F * C * sizeof(float); }
+
 size_t tmgcn_edge_readout_bwd_ws_bytes(int64_t n_rows, int F, int C) {
     // per-row class sums S (n_rows x 2 x C) followed by the per-CTA dU partials
     const size_t s_bytes = ((size_t)(n_rows > 0 ? n_rows : 0) * 2 * C * sizeof(float) + 255) & ~(size_t)255;
-    return s_bytes + (size_t)du_blocks() * 2 * F * C * sizeof(float);
+    return s_bytes + tmgcn_edge_factor_ws_bytes(F, C);
 }
 
-int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
-                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *ws,
-                           void *stream) {
-    TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_readout_bwd: bad sizes");
-    TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_readout_bwd: C=%d outside [1, %d]", C, MAXC);
+int tmgcn_edge_class_sums(const float *dout, const int64_t *inc_ptr, const int64_t *perm, float *S, int64_t n_rows,
+                          int C, void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0, "edge_class_sums: bad sizes");
+    TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_class_sums: C=%d outside [1, %d]", C, MAXC);
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(dout && inc_ptr && S, "edge_class_sums: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = (unsigned)ceil_div(n_rows, 256);
+    if (C <= 2) row_class_sums_kernel<2><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
+    else if (C <= 4) row_class_sums_kernel<4><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
+    else row_class_sums_kernel<8><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
+    return after_launch("row_class_sums");
+}
+
+int tmgcn_edge_factor_apply(const float *y, const float *u, const float *S, float *dy, float *du, int64_t n_rows,
+                            int F, int C, void *ws, void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_factor_apply: bad sizes");
+    TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_factor_apply: C=%d outside [1, %d]", C, MAXC);
     cudaStream_t st = (cudaStream_t)stream;
     const int n_u = 2 * F * C;
     if (n_rows == 0) {
         if (du) TMGCN_CUDA(cudaMemsetAsync(du, 0, (size_t)n_u * sizeof(float), st));
         return 0;
     }
-    TMGCN_REQUIRE(u && dout && inc_ptr && ws && (dy || du), "edge_readout_bwd: null pointer");
-    TMGCN_REQUIRE(!du || y, "edge_readout_bwd: y is required for dU");
-    float *S = (float *)ws;
-    const size_t s_bytes = ((size_t)n_rows * 2 * C * sizeof(float) + 255) & ~(size_t)255;
-    float *partial = du ? (float *)((char *)ws + s_bytes) : nullptr;
-    {   // pass 1
-        const unsigned g = (unsigned)ceil_div(n_rows, 256);
-        if (C <= 2) row_class_sums_kernel<2><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
-        else if (C <= 4) row_class_sums_kernel<4><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
-        else row_class_sums_kernel<8><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
-        if (after_launch("row_class_sums")) return 1;
-    }
+    TMGCN_REQUIRE(u && S && (dy || du), "edge_factor_apply: null pointer");
+    TMGCN_REQUIRE(!du || (y && ws), "edge_factor_apply: y and ws are required for the reduction output");
+    float *partial = du ? (float *)ws : nullptr;
     const bool v4 = F % 4 == 0 && (!dy || (uintptr_t)dy % 16 == 0) && (!y || (uintptr_t)y % 16 == 0);
     const int per_lane = v4 ? 4 : 1;
     const int nch = (F + 32 * per_lane - 1) / (32 * per_lane);
-    TMGCN_REQUIRE(nch <= 4, "edge_readout_bwd: F=%d too large", F);
+    TMGCN_REQUIRE(nch <= 4, "edge_factor_apply: F=%d too large", F);
     const size_t smem = (size_t)n_u * sizeof(float) * (du ? 9 : 1);
-    TMGCN_REQUIRE(smem <= 200 * 1024, "edge_readout_bwd: 2*F*C too large");
+    TMGCN_REQUIRE(smem <= 200 * 1024, "edge_factor_apply: 2*F*C too large");
     int grid = 0;
     // persistent grid = exactly one wave of resident CTAs (a partial second wave would run at low occupancy)
 #define TMGCN_LAUNCH(V, K, CMX)                                                                                   \
     {                                                                                                             \
-        auto kern = readout_bwd_kernel<V, K, CMX>;                                                                \
+        auto kern = (dy && du) ? readout_bwd_kernel<V, K, CMX, true, true>                                        \
+                               : (dy ? readout_bwd_kernel<V, K, CMX, true, false>                                 \
+                                     : readout_bwd_kernel<V, K, CMX, false, true>);                               \
         if (smem > 48 * 1024)                                                                                     \
             TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         int per_sm = 1;                                                                                           \
         TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                      \
         if (per_sm < 1) per_sm = 1;                                                                               \
-        if (per_sm > 4) per_sm = 4;                                                                               \
+        if (du && per_sm > 4) per_sm = 4; /* the dU partial workspace holds 4 CTAs per SM */                      \
         grid = sm_count() * per_sm;                                                                               \
         const int64_t want = ceil_div(n_rows, 8 * 4);                                                             \
         if (grid > want) grid = (int)(want < 1 ? 1 : want);                                                       \
@@ -502,5 +514,17 @@ int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, co
         if (after_launch("reduce_partials_edge")) return 1;
     }
     return 0;
+}
+
+int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
+                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *ws,
+                           void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_readout_bwd: bad sizes");
+    TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_readout_bwd: C=%d outside [1, %d]", C, MAXC);
+    TMGCN_REQUIRE(n_rows == 0 || ws, "edge_readout_bwd: null workspace");
+    float *S = (float *)ws;
+    const size_t s_bytes = ((size_t)(n_rows > 0 ? n_rows : 0) * 2 * C * sizeof(float) + 255) & ~(size_t)255;
+    if (tmgcn_edge_class_sums(dout, inc_ptr, perm, S, n_rows, C, stream)) return 1;
+    return tmgcn_edge_factor_apply(y, u, S, dy, du, n_rows, F, C, ws ? (char *)ws + s_bytes : nullptr, stream);
 }
 }

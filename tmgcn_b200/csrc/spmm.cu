@@ -137,6 +137,70 @@ __global__ void __launch_bounds__(256, MINB) spmm_rows(const int64_t *__restrict
     }
 }
 
+// Skinny operand (F = 4 floats per row, e.g. the 2C-column factor of the low-rank backward): a row gather is
+// a single 16-byte load, so lanes are spread over the NONZEROS of a row instead of over features.  LPR lanes
+// share a row and a warp takes 32/LPR consecutive rows per iteration, so the dependent chain
+// rowptr -> (col, val) -> gather is paid once per 32/LPR rows (warp-per-row was latency-bound: 20 ms for
+// 1.2 G nonzeros); the rows' nonzeros are contiguous, so the (col, val) loads stay coalesced.  The x slice
+// (N * 16 B) is L2-resident.
+template <int ACT, int LPR>
+__global__ void __launch_bounds__(256, 6) spmm_skinny4(const int64_t *__restrict__ rowptr,
+                                                       const int32_t *__restrict__ col, const float *__restrict__ val,
+                                                       const float *__restrict__ x, float *__restrict__ y,
+                                                       int64_t n_rows, int64_t N) {
+    constexpr int RPW = 32 / LPR;                      // rows per warp iteration
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPR, gl = lane % LPR;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_blk = (n_rows + RPW - 1) / RPW;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (int64_t blk = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < n_blk; blk += warps_total) {
+        const int64_t row = blk * RPW + g;
+        const bool live = row < n_rows;
+        int64_t s = 0, e = 0, xbase = 0;
+        if (live) {
+            s = rowptr[row];
+            e = rowptr[row + 1];
+            xbase = (row / N) * N;
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // 4 passes at a time: all (col, val) loads first, then all gathers -- two dependent latencies per
+        // 4*LPR nonzeros of a row instead of two per LPR
+        for (int64_t k = s + gl; k < e; k += 4 * LPR) {
+            int c[4];
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t kk = k + u * LPR;
+                c[u] = kk < e ? col[kk] : -1;
+                v[u] = kk < e ? val[kk] : 0.f;
+            }
+            float4 xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                xv[u] = c[u] >= 0 ? __ldg(x4 + xbase + c[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc.x = fmaf(v[u], xv[u].x, acc.x);
+                acc.y = fmaf(v[u], xv[u].y, acc.y);
+                acc.z = fmaf(v[u], xv[u].z, acc.z);
+                acc.w = fmaf(v[u], xv[u].w, acc.w);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (live && gl == 0) {
+            vact<ACT>(acc);
+            reinterpret_cast<float4 *>(y)[row] = acc;
+        }
+    }
+}
+
 template <int VEC, int G>
 static int launch_spmm_act(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y,
                            int64_t n_rows, int64_t N, int F, int act, cudaStream_t st) {
@@ -185,6 +249,19 @@ extern "C" int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const f
     cudaStream_t st = (cudaStream_t)stream;
     const bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     const bool a8 = ((uintptr_t)x % 8 == 0) && ((uintptr_t)y % 8 == 0);
+    if (F == 4 && a16) {
+        int64_t blocks = ceil_div(n_rows, 8 * 4);
+        const int64_t cap = (int64_t)sm_count() * 6 * 8;
+        if (blocks > cap) blocks = cap;
+        switch (act) {
+            case TMGCN_ACT_NONE: spmm_skinny4<TMGCN_ACT_NONE, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
+            case TMGCN_ACT_RELU: spmm_skinny4<TMGCN_ACT_RELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
+            case TMGCN_ACT_LEAKY: spmm_skinny4<TMGCN_ACT_LEAKY, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
+            case TMGCN_ACT_SELU: spmm_skinny4<TMGCN_ACT_SELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
+            default: set_error("spmm: unknown activation %d", act); return 1;
+        }
+        return after_launch("spmm_skinny4");
+    }
     if (F % 4 == 0 && a16) return launch_spmm_g<4>(rowptr, col, val, x, y, n_rows, N, F, act, st);
     if (F % 2 == 0 && a8) return launch_spmm_g<2>(rowptr, col, val, x, y, n_rows, N, F, act, st);
     return launch_spmm_g<1>(rowptr, col, val, x, y, n_rows, N, F, act, st);
