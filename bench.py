@@ -248,19 +248,34 @@ def run_ours(args):
     dU_host = torch.empty(2 * F, C).pin_memory()
     slice_edges_local = At.nnz
     comm = sharding.ShardComm(b - 1, rank, world, dev) if world > 1 else None
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_h2d, ev_fwd, ev_prev = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     def one_step(e2e):
+        main = torch.cuda.current_stream()
         if e2e:
-            dOut.copy_(dOut_host, non_blocking=True)
+            # host -> device copy of this step's loss gradient on the copy stream: it is only needed by
+            # the backward, so it overlaps the forward (after the previous step has released the buffer)
+            ev_prev.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_prev)
+                dOut.copy_(dOut_host, non_blocking=True)
+                ev_h2d.record(copy_stream)
         # with several ranks the halo exchange (fwd and bwd) and the dW/dU all-reduce run on the
         # communication stream inside forward()/backward(), overlapped with interior slices
         step.forward(H, W, U, comm)
+        if e2e:
+            ev_fwd.record(main)
+            with torch.cuda.stream(copy_stream):        # logits go back while the backward runs
+                copy_stream.wait_event(ev_fwd)
+                out_host.copy_(step.out, non_blocking=True)
+            main.wait_event(ev_h2d)
         dH, dW, dU = step.backward(dOut, W, U, comm)
         if e2e:
-            out_host.copy_(step.out, non_blocking=True)
             dW_host.copy_(dW, non_blocking=True)
             dU_host.copy_(dU, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            main.synchronize()
+            copy_stream.synchronize()                   # the step's results are on the host
         return dH
 
     def barrier():
