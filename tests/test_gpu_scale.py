@@ -160,7 +160,8 @@ def test_scale_adjoint_identities(tg, big):
     dp, dw = ops.gemm_bwd_raw(x[0].contiguous(), W, None, y[0].contiguous(), 0)
     lhs, rhs = dot(got, y[0]), dot(x[0], dp)
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
-    assert relerr(dw, x[0].t() @ y[0]) <= TOL_GRAD
+    # 2M-row reduction: the tensor-core partial sums are flushed every 2048 rows and added in rounded fp32
+    assert relerr(dw, x[0].double().t() @ y[0].double()) <= 2e-5
     # readout: <R(Y), d> = <Y, R^T(d)> and linearity in U
     from tmgcn_b200 import synth
     E, Cc = 500_000, 2

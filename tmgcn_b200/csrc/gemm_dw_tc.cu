@@ -12,8 +12,12 @@
 //       way and writes row n (32 k-values = one 128-byte swizzle row) of a K-major SWIZZLE_128B
 //       shared-memory operand, split into hi and lo.
 // Raw 32-row chunks of P and dY are contiguous 16 KB blocks: one TMA bulk copy each.
-// The accumulator stays in TMEM for the whole kernel; each CTA writes one partial
-// (KI x NO) and a second kernel sums the partials in fixed order (deterministic dW).
+// The tensor core's fp32 accumulation is not round-to-nearest: over hundreds of thousands of rows the
+// error grows linearly (measured 1e-4 at 13K rows per CTA, i.e. ~3e-3 at the 64M-row benchmark shard), so a
+// TMEM accumulator only ever sums DW_FLUSH chunks (2048 rows); four epilogue warps then add it into an fp32
+// shared-memory accumulator with ordinary rounded adds while the MMAs continue into the second TMEM
+// accumulator.  Each CTA writes one partial (KI x NO) and a second kernel sums the partials in fixed
+// order (deterministic dW).
 // The kernel streams P and dY exactly once: 8*N*F bytes per slice.
 #include "tc_common.cuh"
 
@@ -21,9 +25,11 @@ namespace tmgcn {
 namespace tc {
 
 constexpr int DW_KC = 32;                        // rows per chunk (MMA K = 8 => 4 steps)
-constexpr int DW_STAGES = 3;
-constexpr int DW_THREADS = 384;
-constexpr uint32_t DW_TMEM_D = 0, DW_TMEM_A = 128;   // A stage s: [128 + 64 s, +32) hi, [+32, +64) lo
+constexpr int DW_STAGES = 2;
+constexpr int DW_FLUSH = 64;                     // chunks (2048 rows) accumulated in TMEM before a flush
+constexpr int DW_THREADS = 512;
+// two accumulators (one being flushed while the other accumulates), then the A stages
+constexpr uint32_t DW_TMEM_D = 0, DW_TMEM_A = 256;   // A stage s: [256 + 64 s, +32) hi, [+32, +64) lo
 
 struct DwParams {
     const float *p;     // (R, KI)
@@ -44,14 +50,16 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
     uint8_t *b_lo = b_hi + DW_STAGES * b_bytes;
     uint8_t *raw_p = b_lo + DW_STAGES * b_bytes;
     uint8_t *raw_d = raw_p + DW_STAGES * rawp_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(raw_d + DW_STAGES * rawd_bytes);
+    float *accs = reinterpret_cast<float *>(raw_d + DW_STAGES * rawd_bytes);   // [NO][128] column-major fp32 sum
+    uint64_t *bars = reinterpret_cast<uint64_t *>(accs + 128 * NO);
     uint64_t *raw_full = bars;                     // [S]  TMA landed
     uint64_t *rawp_empty = bars + DW_STAGES;       // [S]  A converters done reading raw P
     uint64_t *rawd_empty = bars + 2 * DW_STAGES;   // [S]  B converters done reading raw dY
     uint64_t *ab_full = bars + 3 * DW_STAGES;      // [S]  A (TMEM) and B (smem) operands ready (8 warp arrivals)
     uint64_t *ab_empty = bars + 4 * DW_STAGES;     // [S]  MMAs that read stage s retired
-    uint64_t *d_full = bars + 5 * DW_STAGES;       // [1]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 * DW_STAGES + 1);
+    uint64_t *d_full = bars + 5 * DW_STAGES;       // [2]  a TMEM accumulator holds a finished group of chunks
+    uint64_t *d_empty = bars + 5 * DW_STAGES + 2;  // [2]  ... and has been added into accs
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 * DW_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -62,7 +70,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
             mbar_init(&ab_full[s], 8);
             mbar_init(&ab_empty[s], 1);
         }
-        mbar_init(d_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&d_full[i], 1);
+            mbar_init(&d_empty[i], 4);
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -97,20 +108,25 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
         const uint32_t bhi0 = smem_u32(b_hi), blo0 = smem_u32(b_lo);
         for (int64_t i = 0; i < n_my; ++i) {
             const int s = (int)(i % DW_STAGES);
+            const int64_t grp = i / DW_FLUSH;
+            const int in_grp = (int)(i % DW_FLUSH);
+            const int acc = (int)(grp & 1);
+            if (in_grp == 0) mbar_wait(&d_empty[acc], (uint32_t)(((grp >> 1) & 1) ^ 1));
             mbar_wait(&ab_full[s], (uint32_t)((i / DW_STAGES) & 1));
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_hi = tmem_base + DW_TMEM_A + s * 64, a_lo = a_hi + 32;
+                const uint32_t d_tmem = tmem_base + DW_TMEM_D + acc * 128;
 #pragma unroll
                 for (int j = 0; j < DW_KC / 8; ++j) {
                     const uint64_t dhi = make_desc_sw128(bhi0 + s * b_bytes + j * 32, 16, 1024);
                     const uint64_t dlo = make_desc_sw128(blo0 + s * b_bytes + j * 32, 16, 1024);
-                    mma_tf32_ts(tmem_base + DW_TMEM_D, a_hi + j * 8, dlo, idesc, (i | j) ? 1u : 0u);
-                    mma_tf32_ts(tmem_base + DW_TMEM_D, a_lo + j * 8, dhi, idesc, 1u);
-                    mma_tf32_ts(tmem_base + DW_TMEM_D, a_hi + j * 8, dhi, idesc, 1u);
+                    mma_tf32_ts(d_tmem, a_hi + j * 8, dlo, idesc, (in_grp | j) ? 1u : 0u);
+                    mma_tf32_ts(d_tmem, a_lo + j * 8, dhi, idesc, 1u);
+                    mma_tf32_ts(d_tmem, a_hi + j * 8, dhi, idesc, 1u);
                 }
                 tc_commit(&ab_empty[s]);
-                if (i == n_my - 1) tc_commit(d_full);
+                if (in_grp == DW_FLUSH - 1 || i == n_my - 1) tc_commit(&d_full[acc]);
             }
             __syncwarp();
         }
@@ -145,7 +161,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
                 mbar_arrive(&ab_full[s]);
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // ================= B converters: column n of raw dY -> row n of a K-major SWIZZLE_128B tile =====
         // (tf32 MN-major operands would need the SW128_32B layout; transposing here keeps the layout the
         //  forward kernel uses: row n = 32 k-values = one 128-byte swizzle row, 8-row groups 1024 B apart)
@@ -182,37 +198,44 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gemm_dw_tf32x3_kernel(const DwP
         }
     }
 
-    // ================= epilogue: D -> partial[blockIdx.x] =================
-    if (warp >= 4 && warp < 8) {
+    else if (warp >= 12) {
+        // ================= flush warps: TMEM accumulator -> rounded fp32 adds into accs -> partial =========
         const int q = warp & 3;
-        const int ki = q * 32 + lane;
-        float *dst = p.partial + ((int64_t)blockIdx.x * KI + ki) * NO;
-        if (n_my > 0) {
-            mbar_wait(d_full, 0);
+        const int ki = q * 32 + lane;                      // TMEM lane == row of dW
+        for (int c = 0; c < NO; ++c) accs[c * 128 + ki] = 0.f;     // column-major: conflict-free by lane
+        const int64_t n_groups = (n_my + DW_FLUSH - 1) / DW_FLUSH;
+        for (int64_t grp = 0; grp < n_groups; ++grp) {
+            const int acc = (int)(grp & 1);
+            mbar_wait(&d_full[acc], (uint32_t)((grp >> 1) & 1));
             tc_fence_after();
-            const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + DW_TMEM_D;
+            const uint32_t t_d = tmem_base + ((uint32_t)(q * 32) << 16) + DW_TMEM_D + acc * 128;
             for (int c = 0; c < NO / 16; ++c) {
                 uint32_t v[16];
                 tmem_ld16(t_d + c * 16, v);
                 tmem_wait_ld();
-                if (ki < KI) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        *reinterpret_cast<uint4 *>(dst + c * 16 + k4 * 4) =
-                            make_uint4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-                }
+                for (int k = 0; k < 16; ++k) accs[(c * 16 + k) * 128 + ki] += __uint_as_float(v[k]);
             }
-        } else if (ki < KI) {
-            for (int c = 0; c < NO; ++c) dst[c] = 0.f;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[acc]);
+        }
+        if (ki < KI) {
+            float *dst = p.partial + ((int64_t)blockIdx.x * KI + ki) * NO;
+            for (int c = 0; c < NO; c += 4)
+                *reinterpret_cast<float4 *>(dst + c) = make_float4(accs[c * 128 + ki], accs[(c + 1) * 128 + ki],
+                                                                  accs[(c + 2) * 128 + ki], accs[(c + 3) * 128 + ki]);
         }
     }
+
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 static size_t dw_smem_bytes(int KI, int NO) {
-    return (size_t)DW_STAGES * (2 * DW_KC * NO * 4 + DW_KC * KI * 4 + DW_KC * NO * 4) + 32 * 8 + 1024;
+    return (size_t)DW_STAGES * (2 * DW_KC * NO * 4 + DW_KC * KI * 4 + DW_KC * NO * 4) + (size_t)128 * NO * 4 +
+           32 * 8 + 1024;
 }
 
 }  // namespace tc
