@@ -32,7 +32,7 @@ last one expands to F columns:
     Q'  = M^T x_3 Q   (transposed stencil)      halo exchange = (b-1) * N * 2C floats
     dH  = Q' . V,  V = U~ W^T                   the only F-wide write of the backward
 
-Same gradients to rounding (tested against the oracle and against the dense path); it replaces
+Same gradients to rounding (parity-tested against the CPU restatement of the reference and against the dense path); it replaces
 ~200 GB of HBM traffic per 32-slice shard by ~70 GB.
 """
 from __future__ import annotations
@@ -150,15 +150,10 @@ class LayerStep:
         self._mark("gemm_bwd")
         _lib.check(lib.tmgcn_edge_factor_apply(_p(P), _p(self.G), _p(self.S), None, _p(self.G), T * N, Fi, C,
                                                _p(self.fac_ws), st))
-        # tiny (2C x F) algebra: U~[(h,c), f] = U[hFo+f, c];  dW = G~^T U~;  dU_h = W^T G_h;  V = U~ W^T
-        Ut = U.view(2, Fo, C).permute(0, 2, 1).reshape(J, Fo).contiguous()
-        Gt = self.G.view(2, Fi, C).permute(0, 2, 1).reshape(J, Fi)
-        ops_gemm = ops.gemm_fwd_raw
-        self.dW.copy_(ops_gemm(Gt.t().contiguous(), Ut))                                   # (Fi, J) . (J, Fo)
-        Wt = W.t().contiguous()
-        self.dU.copy_(torch.cat([ops_gemm(Wt, self.G[:Fi].contiguous()), ops_gemm(Wt, self.G[Fi:].contiguous())]))
-        V = ops_gemm(Ut, Wt)                                                                # (J, Fi)
-        Vu = V.view(2, C, Fi).permute(0, 2, 1).reshape(2 * Fi, C).contiguous()              # "U layout"
+        # tiny (2C x F) algebra: dW = G~^T U~, dU_h = W^T G_h, V = U~ W^T
+        dW_, dU_, Vu = ops.lowrank_small(W, U, self.G)
+        self.dW.copy_(dW_)
+        self.dU.copy_(dU_)
         if comm is not None:
             comm.start_allreduce([self.dW, self.dU])
         self._mark("spmm_bwd")

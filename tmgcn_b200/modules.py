@@ -141,8 +141,8 @@ class EmbeddingGCN(_Base):
             plan = EdgePlan(edges, self.N)
         else:
             AtXt, plan = self.AtXt, self.edge_plan
-        Y = ops.gemm_xw(AtXt, self.W)                         # ref: ehf:222
-        return ops.edge_readout(Y, self.U, plan)              # ref: ehf:228-232
+        # ref: ehf:222 (GEMM) + ehf:228-232 (readout): a linear map followed by a C-class readout
+        return ops.propagate_linear_readout(AtXt, self.W, self.U, None, None, plan)
 
 
 class EmbeddingGCN2(_Base):
@@ -192,13 +192,14 @@ class EmbeddingGCN2(_Base):
         else:
             AtXt, plan = self.AtXt, self.edge_plan
         Y = ops.gemm_xw(AtXt, self.W1, self.nonlin2)          # layer 1 (ref: ehf:330-335)
-        if self.apply_M_twice:                                # ref: ehf:342-346
+        if self.apply_M_twice and self.apply_M_three_times:   # ref: ehf:342-346
             Z = ops.gemm_xw(ops.spmm(self.At_csr, ops.mtransform_dense(Y, self.band)), self.W2)
-            if self.apply_M_three_times:
-                Z = ops.mtransform_dense(Z, self.band)
-        else:                                                 # ref: ehf:347-349
-            Z = ops.gemm_xw(ops.spmm(self.At_csr, Y), self.W2)
-        return ops.edge_readout(Z, self.U, plan)              # ref: ehf:351-355
+            Z = ops.mtransform_dense(Z, self.band)
+            return ops.edge_readout(Z, self.U, plan)          # ref: ehf:351-355
+        # layer 2 is linear up to the C-class readout (ref: ehf:342-344 / 347-349, 351-355): fused op whose
+        # backward runs on the rank-2C factor of the readout gradient
+        return ops.propagate_linear_readout(Y, self.W2, self.U, self.At_csr,
+                                            self.band if self.apply_M_twice else None, plan)
 
 
 class EmbeddingKWGCN(_Base):
@@ -233,12 +234,10 @@ class EmbeddingKWGCN(_Base):
             plan = EdgePlan(edges, self.N)
         else:
             AX, plan = self.AX, self.edge_plan
-        if self.no_layers == 2:                               # ref: ehf:486-487
+        if self.no_layers == 2:                               # ref: ehf:486-487, 491-495
             Y = ops.gemm_xw(AX, self.W1, self.nonlin2)
-            Z = ops.gemm_xw(ops.spmm(self.A_csr, Y), self.W2)
-        else:
-            Z = ops.gemm_xw(AX, self.W1)
-        return ops.edge_readout(Z, self.U, plan)
+            return ops.propagate_linear_readout(Y, self.W2, self.U, self.A_csr, None, plan)
+        return ops.propagate_linear_readout(AX, self.W1, self.U, None, None, plan)
 
 
 class TMGCNLayer(nn.Module):
@@ -255,7 +254,10 @@ class TMGCNLayer(nn.Module):
         self.W = nn.Parameter(W.detach().to(ops._dev(), torch.float32).contiguous())
         self.U = nn.Parameter(U.detach().to(ops._dev(), torch.float32).contiguous())
 
-    def forward(self, H: torch.Tensor) -> torch.Tensor:
+    def forward(self, H: torch.Tensor, fused: bool = False) -> torch.Tensor:
+        """fused=True (linear layer, unsharded only) takes the low-rank-backward op."""
+        if fused and not self.act and self.halo == 0 and self.t0 == 0 and self.t1 == self.band.T:
+            return ops.propagate_linear_readout(H, self.W, self.U, self.At, self.band, self.edge_plan)
         Ht = ops.mtransform_dense(H, self.band, self.t0, self.t1, self.halo)
         Y = ops.gemm_xw(ops.spmm(self.At, Ht), self.W, self.act)
         return ops.edge_readout(Y, self.U, self.edge_plan)

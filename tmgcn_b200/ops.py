@@ -434,6 +434,91 @@ class _Act(torch.autograd.Function):
         return dx, None
 
 
+# ---- low-rank backward through the readout factor (see layer_step.py for the algebra) ------------
+def class_sums_raw(dout: torch.Tensor, plan: EdgePlan, n_rows: int) -> torch.Tensor:
+    """S[row, h, c] = sum over incident (e, h) of dout[e, c]  -> (n_rows, 2C)."""
+    lib = _lib.load()
+    Cc = dout.shape[1]
+    inc_ptr, perm = plan.incidence(n_rows)
+    S = torch.empty(n_rows, 2 * Cc, dtype=torch.float32, device=dout.device)
+    _lib.check(lib.tmgcn_edge_class_sums(_p(dout.contiguous()), _p(inc_ptr), _p(perm), _p(S), n_rows, Cc, _stream()))
+    return S
+
+
+def factor_reduce_raw(x2d: torch.Tensor, S: torch.Tensor, Cc: int) -> torch.Tensor:
+    """G[(h, f), c] = sum_rows x[row, f] * S[row, h, c]  -> (2F, C)."""
+    lib = _lib.load()
+    F = x2d.shape[1]
+    G = torch.empty(2 * F, Cc, dtype=torch.float32, device=x2d.device)
+    ws = _ws(lib.tmgcn_edge_factor_ws_bytes(F, Cc))
+    _lib.check(lib.tmgcn_edge_factor_apply(_p(x2d), _p(G), _p(S), None, _p(G), x2d.shape[0], F, Cc, _p(ws), _stream()))
+    return G
+
+
+def factor_expand_raw(S: torch.Tensor, Vu: torch.Tensor, F: int, Cc: int) -> torch.Tensor:
+    """out[row, f] = sum_{h,c} S[row, h, c] * Vu[hF + f, c]  -> (n_rows, F)."""
+    lib = _lib.load()
+    out = torch.empty(S.shape[0], F, dtype=torch.float32, device=S.device)
+    _lib.check(lib.tmgcn_edge_factor_apply(None, _p(Vu), _p(S), _p(out), None, S.shape[0], F, Cc, None, _stream()))
+    return out
+
+
+def lowrank_small(W: torch.Tensor, U: torch.Tensor, G: torch.Tensor):
+    """The (2C x F)-sized algebra of the low-rank backward: U~[(h,c), f] = U[hFo+f, c];
+    dW = G~^T U~, dU_h = W^T G_h, V = U~ W^T (returned in the "U layout" factor_expand wants)."""
+    Fi, Fo = W.shape
+    Cc = U.shape[1]
+    J = 2 * Cc
+    Ut = U.view(2, Fo, Cc).permute(0, 2, 1).reshape(J, Fo).contiguous()
+    Gt = G.view(2, Fi, Cc).permute(0, 2, 1).reshape(J, Fi)
+    dW = gemm_fwd_raw(Gt.t().contiguous(), Ut)                                   # (Fi, J) . (J, Fo)
+    Wt = W.t().contiguous()
+    dU = torch.cat([gemm_fwd_raw(Wt, G[:Fi].contiguous()), gemm_fwd_raw(Wt, G[Fi:].contiguous())])
+    V = gemm_fwd_raw(Ut, Wt)                                                     # (J, Fi)
+    Vu = V.view(2, Cc, Fi).permute(0, 2, 1).reshape(2 * Fi, Cc).contiguous()
+    return dW, dU, Vu
+
+
+class _PropagateLinearReadout(torch.autograd.Function):
+    """out = readout( (A~_t . [M x_3] H) W , U ) for a LINEAR layer (no activation between W and the
+    readout: layer 2 of the reference models, ehf:342-355 / 347-355 / 486-495).  Forward = the usual
+    kernels; backward = the low-rank chain: nothing F-wide except one pass over P and the final dH."""
+
+    @staticmethod
+    def forward(ctx, H, W, U, csr, band, plan):
+        H, W, U = H.contiguous(), W.contiguous(), U.contiguous()
+        Ht = stencil_fwd(H, band) if band is not None else H
+        P = spmm_raw(csr, Ht) if csr is not None else Ht
+        Y = gemm_fwd_raw(P, W)
+        out = readout_fwd_raw(Y.reshape(-1, Y.shape[-1]), plan, U)
+        ctx.csr, ctx.band, ctx.plan, ctx.shape = csr, band, plan, H.shape
+        ctx.save_for_backward(P, W, U)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        P, W, U = ctx.saved_tensors
+        Fi, Cc = W.shape[0], U.shape[1]
+        n_rows = P.numel() // Fi
+        S = class_sums_raw(g, ctx.plan, n_rows)
+        G = factor_reduce_raw(P.reshape(n_rows, Fi), S, Cc)
+        dW, dU, Vu = lowrank_small(W, U, G)
+        dH = None
+        if ctx.needs_input_grad[0]:
+            Q = S.view(ctx.shape[0], ctx.shape[1], 2 * Cc)
+            if ctx.csr is not None:
+                Q = spmm_raw(ctx.csr.transpose(), Q)
+            if ctx.band is not None:
+                Q = stencil_bwd(Q, ctx.band)
+            dH = factor_expand_raw(Q.reshape(n_rows, 2 * Cc), Vu, Fi, Cc).view(ctx.shape)
+        return dH, dW, dU, None, None, None
+
+
+def propagate_linear_readout(H, W, U, csr, band, plan):
+    """Differentiable fused linear layer + readout; csr / band may be None (skip SpMM / M-transform)."""
+    return _PropagateLinearReadout.apply(H, W, U, csr, band, plan)
+
+
 def mtransform_dense(x, band: Band, t0=0, t1=None, halo=0):
     """X~ = X x_3 M (ref: ehf:204), differentiable."""
     return _Stencil.apply(x, band, t0, t1, halo)
