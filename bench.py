@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--act", default="none")
     ap.add_argument("--bwd", default="auto", choices=["auto", "dense", "lowrank"],
                     help="backward formulation (auto = low-rank when the layer is linear, see layer_step.py)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU forward halo: fused into the stencil over NVLink peer memory, or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-nodes", type=int, default=100_000, help="bounded CPU sample: nodes")
     ap.add_argument("--cpu-slices", type=int, default=8)
@@ -235,8 +237,19 @@ def run_ours(args):
     step = LayerStep(At, band, plan, F, F, C, args.act, t0, t1, halo, bwd_mode=args.bwd)
     torch.cuda.empty_cache()
     gen = torch.Generator(device=dev).manual_seed(SEED + 100 + rank)
-    H = torch.empty(T_local + halo, N, F, device=dev)
-    for t in range(T_local + halo):
+    peer, halo_mode = None, ("none" if world == 1 else args.halo)
+    if world > 1 and args.halo == "peer":
+        try:        # layer input in symmetric memory: the boundary stencil reads the predecessor's HBM over NVLink
+            peer = sharding.PeerHalo(T_local, N, F, b - 1, rank, world, dev)
+        except Exception as ex:  # pragma: no cover - depends on the box
+            print(f"[bench] symmetric memory unavailable ({ex}); falling back to the NCCL halo", file=sys.stderr)
+            halo_mode = "nccl"
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer, halo_mode = None, "nccl"
+    H = peer.H if peer is not None else torch.empty(T_local + halo, N, F, device=dev)
+    for t in range(H.shape[0]):
         H[t].copy_(torch.rand(N, F, generator=gen, device=dev))
     gw = torch.Generator().manual_seed(SEED)
     W = (torch.randn(F, F, generator=gw) / F ** 0.5).to(dev)
@@ -263,7 +276,7 @@ def run_ours(args):
                 ev_h2d.record(copy_stream)
         # with several ranks the halo exchange (fwd and bwd) and the dW/dU all-reduce run on the
         # communication stream inside forward()/backward(), overlapped with interior slices
-        step.forward(H, W, U, comm)
+        step.forward(H, W, U, comm, peer)
         if e2e:
             ev_fwd.record(main)
             with torch.cuda.stream(copy_stream):        # logits go back while the backward runs
@@ -371,6 +384,9 @@ def run_ours(args):
                             "H, A~ and the edge list stay device-resident as the reference's ctor caches them "
                             "(ehf:195-198)"},
             "gpu_launches": launches,
+            "halo": {"forward": halo_mode,
+                     "note": "peer = boundary stencil loads the predecessor's b-1 slices from its HBM over NVLink "
+                             "(symmetric memory), fused into the kernel; nccl = send/recv on a side stream"},
             "backward": {"mode": step.bwd_mode,
                          "note": "lowrank = exact re-association of the backward through the rank-2C factor the "
                                  "C-class readout hands back (linear layer, act=none); dense = general path",

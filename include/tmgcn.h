@@ -95,6 +95,12 @@ int tmgcn_mtransform_dense_fwd(const float *x_in, float *x_out, int T_out, int h
                                const float *band_w, int b, void *stream);
 int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream);
+/* forward with the input in two pieces: the `halo` predecessor slices at x_halo, the own slices at x_own.
+ * x_halo may point into a PEER GPU's memory (CUDA IPC / symmetric memory mapped over NVLink): the halo
+ * exchange is then fused into the stencil -- the kernel loads the predecessor's slices straight from its
+ * HBM, no staging copy and no halo region in the local tensor. */
+int tmgcn_mtransform_dense_fwd_split(const float *x_halo, const float *x_own, float *x_out, int T_out, int halo,
+                                     int64_t NF, const float *band_w, int b, void *stream);
 /* same, but only input slices s in [s_begin, s_end) of g_in are written (the others are left untouched):
  * lets a rank produce the `halo` slices it owes its predecessor first (and put them on the wire) and the
  * rest later, in place, without a staging copy. */

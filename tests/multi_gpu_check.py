@@ -66,6 +66,17 @@ def main():
         dH, dW, dU = step.backward(dOut[esel].contiguous(), W, U, comm)
         torch.cuda.synchronize()
     assert torch.equal(Hl[:halo].cpu(), H[t0 - halo:t0]), "forward halo content"
+    # the same forward with the halo exchange fused into the stencil over NVLink peer memory
+    peer = sharding.PeerHalo(Tl, N, F, b - 1, rank, world, dev)
+    peer.H.copy_(H[t0:t1].to(dev))
+    for _ in range(2):
+        out_p = step.forward(peer.H, W, U, comm, peer).clone()
+        torch.cuda.synchronize()
+    assert torch.equal(out_p, out), "peer-memory halo: forward differs from the NCCL halo path"
+    dH_p, dW_p, dU_p = step.backward(dOut[esel].contiguous(), W, U, comm)
+    torch.cuda.synchronize()
+    assert torch.equal(dW_p, dW) and torch.equal(dU_p, dU)
+    print(f"rank {rank}: peer-memory fused halo == NCCL halo (bit-identical logits)", flush=True)
 
     # reference: the whole tensor on one GPU
     ok = True

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "tmgcn_csr_transpose_run": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _p, _p]),
     "tmgcn_mtransform_dense_fwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_bwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
+    "tmgcn_mtransform_dense_fwd_split": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_bwd_range": (_i, [_p, _p, _i, _i, _l, _p, _i, _i, _i, _p]),
     "tmgcn_spmm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _l, _i, _i, _p]),
     "tmgcn_gemm_xw_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),

@@ -63,7 +63,8 @@ __device__ __forceinline__ void load_weights(float *sw, const float *__restrict_
 // forward walks it upwards reading x and writing y, the backward walks it
 // downwards reading gy and writing gx.
 template <int B, int V, bool REVERSE>
-__global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ src, float *__restrict__ dst,
+__global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ src_halo,
+                                                      const float *__restrict__ src, float *__restrict__ dst,
                                                       int T_out, int halo, int64_t n_vec,
                                                       const float *__restrict__ band_w, int b, int s_begin, int s_end) {
     using VT = typename Vec<V>::T;
@@ -72,7 +73,10 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
     load_weights<B>(sw, band_w, T_out, b);
     const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n_vec) return;
-    const VT *in = reinterpret_cast<const VT *>(src) + pos;
+    // forward: the first `halo` input slices come from src_halo (which may be a peer GPU's memory mapped
+    // over NVLink: the halo exchange is then fused into this kernel), the rest from src
+    const VT *in_halo = reinterpret_cast<const VT *>(src_halo) + pos;
+    const VT *in = reinterpret_cast<const VT *>(src) + pos - (REVERSE ? 0 : (int64_t)halo * n_vec);
     VT *out = reinterpret_cast<VT *>(dst) + pos;
     const int T_in = halo + T_out;
     VT ring[R];
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
                     const int u = u0 + q + k;  // step number
                     if (!REVERSE) {
                         // entering element: x[u]
-                        if (u < T_in) ring[q + k] = ld_v(in + (int64_t)u * n_vec);
+                        if (u < T_in) ring[q + k] = ld_v((u < halo ? in_halo : in) + (int64_t)u * n_vec);
                     } else {
                         // entering element: gy[t0], t0 = (T_in-1-u) - halo  (absent for the halo slices)
                         const int t0 = T_in - 1 - u - halo;
@@ -130,24 +134,25 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
 }
 
 template <int B, int V, bool REVERSE>
-static int launch_stencil(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
-                          int s_begin, int s_end, cudaStream_t st) {
+static int launch_stencil(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
+                          const float *band_w, int b, int s_begin, int s_end, cudaStream_t st) {
     const int64_t n_vec = NF / V;
     const size_t smem = (size_t)(T_out + 2 * B) * B * sizeof(float);
     TMGCN_REQUIRE(smem <= 200 * 1024, "mtransform_dense: T_out=%d too large for the weight table (b=%d)", T_out, b);
     auto kern = stencil_kernel<B, V, REVERSE>;
     if (smem > 48 * 1024) TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = 256;
-    kern<<<(unsigned)ceil_div(n_vec, threads), threads, smem, st>>>(src, dst, T_out, halo, n_vec, band_w, b, s_begin,
-                                                                    s_end);
+    kern<<<(unsigned)ceil_div(n_vec, threads), threads, smem, st>>>(src_halo, src, dst, T_out, halo, n_vec, band_w, b,
+                                                                    s_begin, s_end);
     return after_launch(REVERSE ? "stencil_bwd" : "stencil_fwd");
 }
 
 template <int V, bool REVERSE>
-static int dispatch_b(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
-                      int s_begin, int s_end, cudaStream_t st) {
-#define TMGCN_CASE(BB) \
-    if (b <= BB) return launch_stencil<BB, V, REVERSE>(src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
+static int dispatch_b(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
+                      const float *band_w, int b, int s_begin, int s_end, cudaStream_t st) {
+#define TMGCN_CASE(BB)                                                                                             \
+    if (b <= BB)                                                                                                   \
+        return launch_stencil<BB, V, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
     TMGCN_CASE(1)
     TMGCN_CASE(2)
     TMGCN_CASE(4)
@@ -165,17 +170,18 @@ static int dispatch_b(const float *src, float *dst, int T_out, int halo, int64_t
 }
 
 template <bool REVERSE>
-static int stencil_entry(const float *src, float *dst, int T_out, int halo, int64_t NF, const float *band_w, int b,
-                         int s_begin, int s_end, void *stream) {
+static int stencil_entry(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
+                         const float *band_w, int b, int s_begin, int s_end, void *stream) {
     TMGCN_REQUIRE(T_out >= 0 && NF >= 0 && halo >= 0, "mtransform_dense: negative size");
     TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform_dense: band width b=%d outside [1, 32]", b);
     TMGCN_REQUIRE(halo <= b - 1, "mtransform_dense: halo=%d exceeds b-1=%d", halo, b - 1);
     if (NF == 0 || halo + T_out == 0) return 0;
     TMGCN_REQUIRE(src && dst && band_w, "mtransform_dense: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec4 = (NF % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-    if (vec4) return dispatch_b<4, REVERSE>(src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
-    return dispatch_b<1, REVERSE>(src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
+    const bool vec4 = (NF % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) &&
+                      ((uintptr_t)src_halo % 16 == 0);
+    if (vec4) return dispatch_b<4, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
+    return dispatch_b<1, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
 }
 
 }  // namespace tmgcn
@@ -183,11 +189,22 @@ static int stencil_entry(const float *src, float *dst, int T_out, int halo, int6
 extern "C" {
 int tmgcn_mtransform_dense_fwd(const float *x_in, float *x_out, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream) {
-    return tmgcn::stencil_entry<false>(x_in, x_out, T_out, halo, NF, band_w, b, 0, halo + T_out, stream);
+    // contiguous [halo | own] input: the own part starts `halo` slices in
+    return tmgcn::stencil_entry<false>(x_in, x_in ? x_in + (int64_t)halo * NF : x_in, x_out, T_out, halo, NF, band_w, b,
+                                       0, halo + T_out, stream);
+}
+int tmgcn_mtransform_dense_fwd_split(const float *x_halo, const float *x_own, float *x_out, int T_out, int halo,
+                                     int64_t NF, const float *band_w, int b, void *stream) {
+    if (halo > 0 && !x_halo) {
+        tmgcn::set_error("mtransform_dense_fwd_split: null halo pointer");
+        return 1;
+    }
+    return tmgcn::stencil_entry<false>(halo > 0 ? x_halo : x_own, x_own, x_out, T_out, halo, NF, band_w, b, 0,
+                                       halo + T_out, stream);
 }
 int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream) {
-    return tmgcn::stencil_entry<true>(g_out, g_in, T_out, halo, NF, band_w, b, 0, halo + T_out, stream);
+    return tmgcn::stencil_entry<true>(g_out, g_out, g_in, T_out, halo, NF, band_w, b, 0, halo + T_out, stream);
 }
 int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                      const float *band_w, int b, int s_begin, int s_end, void *stream) {
@@ -195,6 +212,6 @@ int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out,
         tmgcn::set_error("mtransform_dense_bwd_range: bad slice range [%d, %d)", s_begin, s_end);
         return 1;
     }
-    return tmgcn::stencil_entry<true>(g_out, g_in, T_out, halo, NF, band_w, b, s_begin, s_end, stream);
+    return tmgcn::stencil_entry<true>(g_out, g_out, g_in, T_out, halo, NF, band_w, b, s_begin, s_end, stream);
 }
 }

@@ -92,41 +92,59 @@ class LayerStep:
             self.hook(name)
 
     # ---- kernels on slice sub-ranges (pointer offsets; rowptr entries are absolute) -----------------
-    def _stencil_fwd(self, H, Ht, t_lo, t_hi):
-        """outputs [t_lo, t_hi) of this shard; inputs start `self.halo + t_lo - hh` slices into H."""
-        hh = min(self.band.b - 1, self.halo + t_lo)
+    def _stencil_fwd(self, H, Ht, t_lo, t_hi, h_in=None):
+        """outputs [t_lo, t_hi) of this shard; H physically starts with `h_in` halo slices (default: all of
+        them; 0 when the halo lives in a peer GPU's memory)."""
+        h_in = self.halo if h_in is None else h_in
+        hh = min(self.band.b - 1, h_in + t_lo)
         NF = self.N * self.F_in
         _lib.check(self.lib.tmgcn_mtransform_dense_fwd(
-            _p(H[self.halo + t_lo - hh:]), _p(Ht[t_lo:]), t_hi - t_lo, hh, NF,
+            _p(H[h_in + t_lo - hh:]), _p(Ht[t_lo:]), t_hi - t_lo, hh, NF,
             _p(self.w_f32[t_lo:]), self.band.b, _stream()))
 
     def _spmm(self, csr, x, y, t_lo, t_hi, F):
         _lib.check(self.lib.tmgcn_spmm_fwd(_p(csr.rowptr[t_lo * self.N:]), _p(csr.col), _p(csr.val), _p(x[t_lo:]),
                                            _p(y[t_lo:]), t_hi - t_lo, self.N, F, 0, _stream()))
 
-    def forward(self, H: torch.Tensor, W: torch.Tensor, U: torch.Tensor, comm=None) -> torch.Tensor:
-        """comm: a sharding.ShardComm -> the forward halo exchange runs on its stream while the slices that
-        do not depend on the halo are transformed and propagated."""
+    def forward(self, H: torch.Tensor, W: torch.Tensor, U: torch.Tensor, comm=None, peer=None) -> torch.Tensor:
+        """comm: a sharding.ShardComm -> the forward halo exchange (NCCL) runs on its stream while the slices
+        that do not depend on the halo are transformed and propagated.
+        peer: a sharding.PeerHalo -> H is the rank's own (T, N, F) block in symmetric memory and the boundary
+        stencil reads the predecessor's slices from peer memory over NVLink (exchange fused into the kernel)."""
         lib, T, N, st = self.lib, self.T, self.N, _stream()
-        assert H.shape == (T + self.halo, N, self.F_in) and H.is_contiguous()
+        h_in = 0 if peer is not None else self.halo
+        assert H.shape == (T + h_in, N, self.F_in) and H.is_contiguous()
         Ht = self._view(self.B1, T, self.F_in)
         P = self._view(self.B2, T, self.F_in)
         Y = self._view(self.B1, T, self.F_out)
-        hb = min(self.band.b - 1, T) if (comm is not None and self.halo > 0) else 0
+        overlap = (comm is not None or peer is not None) and self.halo > 0
+        hb = min(self.band.b - 1, T) if overlap else 0
         if comm is not None:
-            self._mark("halo_fwd_start")
             comm.wait_send_buffer_free()      # last step's gradient halo is sent from B2, which SpMM overwrites below
+        if peer is not None:
+            self._mark("halo_fwd_start")
+            NF = N * self.F_in
+
+            def boundary():     # outputs [0, hb): halo slices from the predecessor's HBM, the rest from ours
+                _lib.check(lib.tmgcn_mtransform_dense_fwd_split(_p(peer.tail()), _p(H), _p(Ht), hb, self.halo, NF,
+                                                                _p(self.w_f32), self.band.b, _stream()))
+            peer.run_boundary(boundary)
+        elif comm is not None:
+            self._mark("halo_fwd_start")
             comm.start_forward(H, T, self.halo)
         if hb < T:
             self._mark("stencil_fwd")
-            self._stencil_fwd(H, Ht, hb, T)
+            self._stencil_fwd(H, Ht, hb, T, h_in)
             self._mark("spmm_fwd")
             self._spmm(self.At, Ht, P, hb, T, self.F_in)
         if hb > 0:
             self._mark("halo_fwd_wait")
-            comm.wait(comm.fwd_done)
-            self._mark("stencil_fwd")
-            self._stencil_fwd(H, Ht, 0, hb)
+            if peer is not None:
+                torch.cuda.current_stream().wait_event(peer.boundary_done)
+            else:
+                comm.wait(comm.fwd_done)
+                self._mark("stencil_fwd")
+                self._stencil_fwd(H, Ht, 0, hb, h_in)
             self._mark("spmm_fwd")
             self._spmm(self.At, Ht, P, 0, hb, self.F_in)
         self._mark("gemm_fwd")

@@ -154,6 +154,45 @@ class ShardComm:
         torch.cuda.current_stream().wait_event(event)
 
 
+class PeerHalo:
+    """Forward halo fused into the stencil over NVLink peer memory.
+
+    Every rank keeps its layer input H (T_own, N, F) in symmetric memory; rank r maps rank r-1's block and
+    the boundary stencil kernel (`tmgcn_mtransform_dense_fwd_split`) loads the predecessor's last b-1 slices
+    straight from its HBM: no NCCL copy, no staging, no halo region in the local tensor.  Two stream-ordered
+    cross-rank barriers per step fence the reads: "every H is ready" before, "all reads are done" after
+    (the owner waits on `reads_done` before it overwrites H)."""
+
+    def __init__(self, T_own: int, N: int, F: int, h: int, rank: int, world: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.T, self.N, self.F, self.h, self.rank, self.world = T_own, N, F, min(h, T_own), rank, world
+        self.buf = symm_mem.empty(T_own * N * F, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, (group or dist.group.WORLD).group_name)
+        self.H = self.buf.view(T_own, N, F)
+        self.prev = self.hdl.get_buffer(rank - 1, (T_own, N, F), torch.float32) if rank > 0 else None
+        self.stream = torch.cuda.Stream(device=device)
+        self.boundary_done = torch.cuda.Event()
+        self.reads_done = torch.cuda.Event()
+        self._ready = torch.cuda.Event()
+
+    def tail(self) -> torch.Tensor:
+        """the predecessor's last h slices -- a view of PEER memory"""
+        return self.prev[self.T - self.h:]
+
+    def run_boundary(self, fn):
+        """fn() launches the peer-reading boundary stencil; runs on the side stream between the two barriers."""
+        main = torch.cuda.current_stream()
+        self._ready.record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._ready)
+            self.hdl.barrier(channel=0)          # every rank's H is complete
+            if self.rank > 0:
+                fn()
+            self.boundary_done.record(self.stream)
+            self.hdl.barrier(channel=1)          # every rank has finished reading its predecessor
+            self.reads_done.record(self.stream)
+
+
 def allreduce_grads(grads: List[torch.Tensor]):
     """Sum the shared-parameter gradients (dW, dU) over ranks."""
     if not grads:
