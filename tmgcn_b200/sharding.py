@@ -111,7 +111,7 @@ class ShardComm:
 
     def __init__(self, h: int, rank: int, world: int, device):
         self.h, self.rank, self.world = h, rank, world
-        self.stream = torch.cuda.Stream(device=device)
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.fwd_done = torch.cuda.Event()
         self.bwd_sent = torch.cuda.Event()
         self.bwd_recv = torch.cuda.Event()
@@ -170,7 +170,8 @@ class PeerHalo:
         self.hdl = symm_mem.rendezvous(self.buf, (group or dist.group.WORLD).group_name)
         self.H = self.buf.view(T_own, N, F)
         self.prev = self.hdl.get_buffer(rank - 1, (T_own, N, F), torch.float32) if rank > 0 else None
-        self.stream = torch.cuda.Stream(device=device)
+        # high priority: the boundary kernel must not queue behind the main stream's persistent SpMM grid
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.boundary_done = torch.cuda.Event()
         self.reads_done = torch.cuda.Event()
         self._ready = torch.cuda.Event()
