@@ -65,5 +65,39 @@ def full(path):
             pass
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] in ("launches", "full"):
     {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+
+
+def traffic(path, out_json, **cfg):
+    """ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum CSV -> per-kernel DRAM
+    bytes per launch (max over the launches seen) as JSON for bench.py's roofline.traffic."""
+    import json
+    with open(path) as f:
+        lines = [l for l in f if l.startswith('"')]
+    r = csv.reader(lines)
+    hdr = next(r)
+    ki, mi, vi, ui, ii = (hdr.index(x) for x in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+    per = {}
+    for row in r:
+        d = per.setdefault(row[ii], {"name": row[ki].split("(")[0]})
+        v = float(row[vi].replace(",", ""))
+        u = row[ui]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(u, 1)
+        d[row[mi]] = v * scale
+    out = {}
+    for d in per.values():
+        b = d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+        k = out.setdefault(d["name"], {"dram_bytes_per_launch": 0.0, "ms": 0.0, "launches": 0})
+        k["launches"] += 1
+        if b > k["dram_bytes_per_launch"]:
+            k["dram_bytes_per_launch"], k["ms"] = b, d.get("gpu__time_duration.sum", 0.0)
+    json.dump({"how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+                      "--clock-control none, largest launch per kernel", "config": cfg, "kernels": out},
+              open(out_json, "w"), indent=1)
+    for k, v in sorted(out.items(), key=lambda kv: -kv[1]["dram_bytes_per_launch"]):
+        print(f"{v['dram_bytes_per_launch'] / 1e9:10.3f} GB {v['ms']:9.3f} ms  {k}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "traffic":
+    traffic(sys.argv[2], sys.argv[3], nodes=2_000_000, slices=32, pairs=10_000_000, rho=0.9, band=10, feat=128)
