@@ -250,17 +250,30 @@ extern "C" int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const f
     const bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     const bool a8 = ((uintptr_t)x % 8 == 0) && ((uintptr_t)y % 8 == 0);
     if (F == 4 && a16) {
-        int64_t blocks = ceil_div(n_rows, 8 * 4);
-        const int64_t cap = (int64_t)sm_count() * 6 * 8;
-        if (blocks > cap) blocks = cap;
-        switch (act) {
-            case TMGCN_ACT_NONE: spmm_skinny4<TMGCN_ACT_NONE, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
-            case TMGCN_ACT_RELU: spmm_skinny4<TMGCN_ACT_RELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
-            case TMGCN_ACT_LEAKY: spmm_skinny4<TMGCN_ACT_LEAKY, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
-            case TMGCN_ACT_SELU: spmm_skinny4<TMGCN_ACT_SELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, val, x, y, n_rows, N); break;
-            default: set_error("spmm: unknown activation %d", act); return 1;
+        // One launch per group of slices whose operand (N * 16 B each) fits comfortably in L2: inside a single
+        // grid-stride launch over all T slices the warps drift apart (measured 138 -> 58 Gnnz/s from T = 6 to
+        // T = 32) until several operand slices compete for L2 and the 16-byte gathers go to DRAM.
+        const int64_t slice_bytes = N * 16;
+        int64_t per_launch = (int64_t)(l2_bytes() / 3) / (slice_bytes > 0 ? slice_bytes : 1);
+        if (per_launch < 1) per_launch = 1;
+        for (int64_t t0 = 0; t0 < T; t0 += per_launch) {
+            const int64_t rows = (t0 + per_launch < T ? per_launch : T - t0) * N;
+            const int64_t *rp = rowptr + t0 * N;
+            const float *xs = x + t0 * N * 4;
+            float *ys = y + t0 * N * 4;
+            int64_t blocks = ceil_div(rows, 8 * 4);
+            const int64_t cap = (int64_t)sm_count() * 6 * 8;
+            if (blocks > cap) blocks = cap;
+            switch (act) {
+                case TMGCN_ACT_NONE: spmm_skinny4<TMGCN_ACT_NONE, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+                case TMGCN_ACT_RELU: spmm_skinny4<TMGCN_ACT_RELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+                case TMGCN_ACT_LEAKY: spmm_skinny4<TMGCN_ACT_LEAKY, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+                case TMGCN_ACT_SELU: spmm_skinny4<TMGCN_ACT_SELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+                default: set_error("spmm: unknown activation %d", act); return 1;
+            }
+            if (after_launch("spmm_skinny4")) return 1;
         }
-        return after_launch("spmm_skinny4");
+        return 0;
     }
     if (F % 4 == 0 && a16) return launch_spmm_g<4>(rowptr, col, val, x, y, n_rows, N, F, act, st);
     if (F % 2 == 0 && a8) return launch_spmm_g<2>(rowptr, col, val, x, y, n_rows, N, F, act, st);
