@@ -224,6 +224,33 @@ def gen_models():
     d["wide_out"], d["wide_dOut"] = out.detach().numpy(), dOut3.numpy()
     for k, v in grads(m, out, dOut3, ["W1", "W2", "U"]).items():
         d["wide_d" + k] = v
+    # per-slice weights (condensed_W=False, ehf:188-191 / 277-282) and the regression head (ehf:359-423)
+    t.manual_seed(500)
+    m = ehf.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=False, use_Minv=False)
+    out = m()
+    d["gcn1u_W"], d["gcn1u_U"], d["gcn1u_out"] = m.W.detach().numpy().copy(), m.U.detach().numpy().copy(), out.detach().numpy()
+    for k, v in grads(m, out, dOut, ["W", "U"]).items():
+        d["gcn1u_d" + k] = v
+    t.manual_seed(600)
+    m = ehf.EmbeddingGCN2(At, X, edges, M, hidden_feat=[6, 6, 2], condensed_W=False, use_Minv=False,
+                          apply_M_twice=True, nonlin2="leaky")
+    out = m()
+    for n in ("W1", "W2", "U"):
+        d["gcn2u_" + n] = getattr(m, n).detach().numpy().copy()
+    d["gcn2u_out"] = out.detach().numpy()
+    for k, v in grads(m, out, dOut, ["W1", "W2", "U"]).items():
+        d["gcn2u_d" + k] = v
+    t.manual_seed(700)
+    m = ehf.EmbeddingGCN_reg(At, X, M, hidden_feat=[6, 2], condensed_W=True, use_Minv=False)
+    out = m()
+    dReg = t.randn(out.shape, generator=g)
+    d["reg_W"], d["reg_lw"], d["reg_lb"] = (m.W.detach().numpy().copy(), m.lin1.weight.detach().numpy().copy(),
+                                            m.lin1.bias.detach().numpy().copy())
+    d["reg_out"], d["reg_dOut"] = out.detach().numpy(), dReg.numpy()
+    for p_ in m.parameters():
+        p_.grad = None
+    out.backward(dReg)
+    d["reg_dW"], d["reg_dlw"], d["reg_dlb"] = m.W.grad.numpy().copy(), m.lin1.weight.grad.numpy().copy(), m.lin1.bias.grad.numpy().copy()
     np.savez_compressed(os.path.join(OUT, "models.npz"), **d)
     print("models.npz", len(d))
 

@@ -437,13 +437,43 @@ def test_module_seed_reproduces_reference_init(tg, golden_models):
     assert torch.equal(k.W1.detach().cpu(), torch.from_numpy(g["kw2_W1"]))
 
 
+def test_module_per_slice_weights_and_regression_head(tg, golden_models):
+    """condensed_W=False (ehf:188-191, 277-282) and EmbeddingGCN_reg (ehf:359-423) against the reference."""
+    g = golden_models
+    T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
+    dOut = torch.from_numpy(g["gcn1_dOut"]).cuda()
+    m = tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=False, use_Minv=False)
+    assert tuple(m.W.shape) == (T, 2, 6)
+    _load(m, g, "gcn1u_", ["W", "U"])
+    out = m()
+    assert relerr(out, g["gcn1u_out"]) <= TOL_OUT
+    out.backward(dOut)
+    assert relerr(m.W.grad, g["gcn1u_dW"]) <= TOL_GRAD and relerr(m.U.grad, g["gcn1u_dU"]) <= TOL_GRAD
+    m2 = tg.EmbeddingGCN2(At, X, edges, M, hidden_feat=[6, 6, 2], condensed_W=False, use_Minv=False,
+                          apply_M_twice=True, nonlin2="leaky")
+    _load(m2, g, "gcn2u_", ["W1", "W2", "U"])
+    out = m2()
+    assert relerr(out, g["gcn2u_out"]) <= TOL_OUT
+    out.backward(dOut)
+    for n in ("W1", "W2", "U"):
+        assert relerr(getattr(m2, n).grad, g["gcn2u_d" + n]) <= TOL_GRAD, n
+    r = tg.EmbeddingGCN_reg(At, X, M, hidden_feat=[6, 2], condensed_W=True, use_Minv=False)
+    with torch.no_grad():
+        r.W.copy_(torch.from_numpy(g["reg_W"]))
+        r.lin1.weight.copy_(torch.from_numpy(g["reg_lw"]))
+        r.lin1.bias.copy_(torch.from_numpy(g["reg_lb"]))
+    out = r()
+    assert tuple(out.shape) == (T, N) and relerr(out, g["reg_out"]) <= TOL_OUT
+    out.backward(torch.from_numpy(g["reg_dOut"]).cuda())
+    assert relerr(r.W.grad, g["reg_dW"]) <= TOL_GRAD
+    assert relerr(r.lin1.weight.grad, g["reg_dlw"]) <= TOL_GRAD and relerr(r.lin1.bias.grad, g["reg_dlb"]) <= TOL_GRAD
+
+
 def test_module_errors(tg, golden_models):
     g = golden_models
     T, N, M, At, A, X, X2, edges, edges2 = _inputs(g)
     with pytest.raises(NotImplementedError):
         tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=True, use_Minv=True)
-    with pytest.raises(NotImplementedError):
-        tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[6, 2], condensed_W=False, use_Minv=False)
     with pytest.raises(AssertionError):
         tg.func_MProduct(torch.eye(3).reshape(1, 3, 3).to_sparse(), torch.eye(2, dtype=torch.float64))
     with pytest.raises(NotImplementedError):

@@ -6,10 +6,10 @@ C ABI of libtmgcn_b200.so (include/tmgcn.h).  Importing the package does not
 need a GPU; calling anything on the hot path does, and fails loudly without one.
 """
 from . import _lib  # noqa: F401
-from .modules import (EmbeddingGCN, EmbeddingGCN2, EmbeddingKWGCN, TMGCNLayer, create_matrix_M, func_MProduct,
-                      split_slices)
+from .modules import (EmbeddingGCN, EmbeddingGCN2, EmbeddingGCN_reg, EmbeddingKWGCN, TMGCNLayer, create_matrix_M,
+                      func_MProduct, split_slices)
 from .ops import Band, EdgePlan, SliceCSR
 
-__all__ = ["EmbeddingGCN", "EmbeddingGCN2", "EmbeddingKWGCN", "TMGCNLayer", "create_matrix_M", "func_MProduct",
+__all__ = ["EmbeddingGCN", "EmbeddingGCN2", "EmbeddingGCN_reg", "EmbeddingKWGCN", "TMGCNLayer", "create_matrix_M", "func_MProduct",
            "split_slices", "Band", "EdgePlan", "SliceCSR"]
 __version__ = "0.1.0"

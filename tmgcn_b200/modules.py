@@ -6,8 +6,9 @@ create_matrix_M helpers -- backed by libtmgcn_b200.so instead of ATen CPU ops.
 
 Differences a caller can observe (all documented in INTEGRATION.md):
   * results and parameters live on the current CUDA device (fp32);
-  * `use_Minv=True` and `condensed_W=False` raise NotImplementedError (no shipped
-    experiment uses them; SURVEY.md section 8f lists them as "next" rows).
+  * `use_Minv=True` raises NotImplementedError (no shipped experiment uses it; SURVEY.md
+    section 8f lists it as a "next" row); `condensed_W=False` (per-slice weights) runs one GEMM
+    launch per slice.
 """
 from __future__ import annotations
 
@@ -116,15 +117,17 @@ class EmbeddingGCN(_Base):
         super().__init__()
         if use_Minv:
             raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
-        if not condensed_W:
-            raise NotImplementedError("condensed_W=False is outside the accelerated path (SURVEY.md section 8f)")
         self.M = M
         self.band = Band(M)
         self.use_Minv = use_Minv
+        self.condensed_W = condensed_W
         self.T = X.shape[0]
         self.N = X.shape[1]
         self.F = [X.shape[-1]] + hidden_feat
-        self.W = self._param(self.F[0], self.F[1])
+        if condensed_W:                                       # ref: ehf:188-191
+            self.W = self._param(self.F[0], self.F[1])
+        else:
+            self.W = self._param(self.T, self.F[0], self.F[1])
         self.U = self._param(2 * self.F[1], self.F[2])
         self.AtXt = self.compute_AtXt(At, X)                  # ref: ehf:195
         self.edge_plan = EdgePlan(edges, self.N)              # ref: ehf:196-198
@@ -141,6 +144,8 @@ class EmbeddingGCN(_Base):
             plan = EdgePlan(edges, self.N)
         else:
             AtXt, plan = self.AtXt, self.edge_plan
+        if not self.condensed_W:                              # per-slice weights: batched matmul (ehf:222)
+            return ops.edge_readout(ops.gemm_xw_sliced(AtXt, self.W), self.U, plan)
         # ref: ehf:222 (GEMM) + ehf:228-232 (readout): a linear map followed by a C-class readout
         return ops.propagate_linear_readout(AtXt, self.W, self.U, None, None, plan)
 
@@ -153,8 +158,7 @@ class EmbeddingGCN2(_Base):
         super().__init__()
         if use_Minv:
             raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
-        if not condensed_W:
-            raise NotImplementedError("condensed_W=False is outside the accelerated path (SURVEY.md section 8f)")
+        self.condensed_W = condensed_W
         self.At = At
         self.M = M
         self.band = Band(M)
@@ -164,8 +168,12 @@ class EmbeddingGCN2(_Base):
         self.T = X.shape[0]
         self.N = X.shape[1]
         self.F = [X.shape[-1]] + hidden_feat
-        self.W1 = self._param(self.F[0], self.F[1])
-        self.W2 = self._param(self.F[1], self.F[2])
+        if condensed_W:                                       # ref: ehf:277-282
+            self.W1 = self._param(self.F[0], self.F[1])
+            self.W2 = self._param(self.F[1], self.F[2])
+        else:
+            self.W1 = self._param(self.T, self.F[0], self.F[1])
+            self.W2 = self._param(self.T, self.F[1], self.F[2])
         self.U = self._param(self.F[2] * 2, self.F[3])
         self.nonlin2 = _act_name(nonlin2)
         self.At_csr = self._csr(At, self.N)
@@ -191,6 +199,13 @@ class EmbeddingGCN2(_Base):
             plan = EdgePlan(edges, self.N)
         else:
             AtXt, plan = self.AtXt, self.edge_plan
+        if not self.condensed_W:                              # per-slice weights: batched matmuls
+            Y = ops.gemm_xw_sliced(AtXt, self.W1, self.nonlin2)
+            Yt = ops.mtransform_dense(Y, self.band) if self.apply_M_twice else Y
+            Z = ops.gemm_xw_sliced(ops.spmm(self.At_csr, Yt), self.W2)
+            if self.apply_M_twice and self.apply_M_three_times:
+                Z = ops.mtransform_dense(Z, self.band)
+            return ops.edge_readout(Z, self.U, plan)
         Y = ops.gemm_xw(AtXt, self.W1, self.nonlin2)          # layer 1 (ref: ehf:330-335)
         if self.apply_M_twice and self.apply_M_three_times:   # ref: ehf:342-346
             Z = ops.gemm_xw(ops.spmm(self.At_csr, ops.mtransform_dense(Y, self.band)), self.W2)
@@ -200,6 +215,36 @@ class EmbeddingGCN2(_Base):
         # backward runs on the rank-2C factor of the readout gradient
         return ops.propagate_linear_readout(Y, self.W2, self.U, self.At_csr,
                                             self.band if self.apply_M_twice else None, plan)
+
+
+class EmbeddingGCN_reg(_Base):
+    """1-layer TM-GCN with a node-regression head (ref: ehf:359-423): out[t, n] = lin1(AtXt[t, n] @ W).
+    As in the reference, forward() ignores its arguments and always uses the constructor's inputs."""
+
+    def __init__(self, At, X, M, hidden_feat=[2, 2], condensed_W=False, use_Minv=True):
+        super().__init__()
+        if use_Minv:
+            raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
+        self.M = M
+        self.band = Band(M)
+        self.use_Minv = use_Minv
+        self.condensed_W = condensed_W
+        self.T = X.shape[0]
+        self.N = X.shape[1]
+        self.F = [X.shape[-1]] + hidden_feat
+        if condensed_W:
+            self.W = self._param(self.F[0], self.F[1])
+        else:
+            self.W = self._param(self.T, self.F[0], self.F[1])
+        self.lin1 = nn.Linear(self.F[1], 1).to(ops._dev())    # same init draws as the reference's nn.Linear
+        csr = self._csr(At, self.N)
+        with torch.no_grad():
+            self.AtXt = ops.spmm_raw(csr, ops.stencil_fwd(self._x(X), self.band))
+
+    def forward(self, At=None, X=None):
+        Y = ops.gemm_xw(self.AtXt, self.W) if self.condensed_W else ops.gemm_xw_sliced(self.AtXt, self.W)
+        out = ops.gemm_xw(Y, self.lin1.weight.t().contiguous()) + self.lin1.bias     # (T, N, 1)
+        return out.squeeze(2)
 
 
 class EmbeddingKWGCN(_Base):

@@ -534,6 +534,13 @@ def gemm_xw(p, w, act=None):
     return _Gemm.apply(p, w, ACT[act] if not isinstance(act, int) else act)
 
 
+def gemm_xw_sliced(p, w, act=None):
+    """per-slice weights: act(p[t] @ w[t]) for w of shape (T, K, Nf) -- the reference's condensed_W=False
+    batched matmul (ref: ehf:188-191, 222, 277-282, 330); one GEMM launch per slice, differentiable."""
+    assert p.dim() == 3 and w.dim() == 3 and p.shape[0] == w.shape[0]
+    return torch.stack([gemm_xw(p[t], w[t], act) for t in range(p.shape[0])])
+
+
 def edge_readout(y, u, plan: EdgePlan):
     """[y[src] || y[dst]] @ u (ref: ehf:228-232), differentiable."""
     return _Readout.apply(y, u, plan)
