@@ -78,12 +78,29 @@ int tmgcn_mtransform_sparse_run(const int64_t *in_rowptr, const int32_t *in_col,
 /* transpose every slice of a CSR-of-slices (for the backward SpMM).
  * plan: counts[T*N] (zero-initialised by the call) = entries per transposed row.
  * run: given the scanned t_rowptr, fills t_col / t_val with ascending columns.
- * ws: nnz * 8 bytes + T*N*8 bytes (tmgcn_csr_transpose_ws_bytes). */
-size_t tmgcn_csr_transpose_ws_bytes(int64_t n_rows, int64_t nnz);
+ * ws: tmgcn_csr_transpose_ws_bytes(T*N, nnz, val_is_f64) bytes; values fp32 or fp64. */
+size_t tmgcn_csr_transpose_ws_bytes(int64_t n_rows, int64_t nnz, int val_is_f64);
 int tmgcn_csr_transpose_plan(const int64_t *rowptr, const int32_t *col, int T, int64_t N, int64_t *counts,
                              void *stream);
-int tmgcn_csr_transpose_run(const int64_t *rowptr, const int32_t *col, const float *val, int T, int64_t N,
-                            const int64_t *t_rowptr, int32_t *t_col, float *t_val, void *ws, void *stream);
+int tmgcn_csr_transpose_run(const int64_t *rowptr, const int32_t *col, const void *val, int T, int64_t N,
+                            const int64_t *t_rowptr, int32_t *t_col, void *t_val, int val_is_f64, void *ws,
+                            void *stream);
+
+/* ---- graph preparation (the step before (a)) ---------------------------
+ * ref: read_data.py:88-164 -- func_make_symmetric (A + A^T)/2, func_edge_life (a ones-band M-transform:
+ * use tmgcn_mtransform_sparse_*), func_laplacian_transformation D^-1/2 (B + I) D^-1/2.
+ * axpby     : C = alpha*A + beta*B by a sorted 2-way row merge (plan counts, caller scans, run fills);
+ * row_sums  : out[row] = sum of the row's values (fp64);
+ * scale_sym : val[k] *= deg[row]^-1/2 * deg[t*N + col[k]]^-1/2 in place. */
+int tmgcn_csr_axpby_plan(const int64_t *a_rowptr, const int32_t *a_col, const int64_t *b_rowptr, const int32_t *b_col,
+                         int64_t n_rows, int64_t *counts, void *stream);
+int tmgcn_csr_axpby_run(const int64_t *a_rowptr, const int32_t *a_col, const void *a_val, const int64_t *b_rowptr,
+                        const int32_t *b_col, const void *b_val, double alpha, double beta, int64_t n_rows,
+                        const int64_t *c_rowptr, int32_t *c_col, void *c_val, int val_is_f64, void *stream);
+int tmgcn_csr_row_sums(const int64_t *rowptr, const void *val, int64_t n_rows, double *out, int val_is_f64,
+                       void *stream);
+int tmgcn_csr_scale_sym(const int64_t *rowptr, const int32_t *col, void *val, int T, int64_t N, const double *deg,
+                        int val_is_f64, void *stream);
 
 /* ---- (b) dense M-transform  X~ = X x_3 M  (time stencil) ------------------
  * ref: ehf:204 / ehf:308 / ehf:346  (M @ X.reshape(T, N*F)).

@@ -26,6 +26,10 @@ __all__ = [
     "layer_forward",
     "layer_fwd_bwd",
     "normalise_adjacency",
+    "make_symmetric",
+    "edge_life",
+    "laplacian_transformation",
+    "create_sparse",
 ]
 
 
@@ -329,3 +333,61 @@ def normalise_adjacency(idx, val, T, N):
     dinv = 1.0 / np.sqrt(deg)
     v = v * dinv[t * N + r] * dinv[t * N + c]
     return np.stack([t, r, c]).astype(np.int64), v
+
+
+# --------------------------------------------------------------------------
+# graph preparation (the "next" row in front of the sparse M-transform)
+# --------------------------------------------------------------------------
+def _coalesce(t, r, c, v, N):
+    key = (t * N + r) * N + c
+    order = np.argsort(key, kind="stable")
+    key, v = key[order], v[order]
+    first = np.ones(key.shape, bool)
+    first[1:] = key[1:] != key[:-1]
+    starts = np.nonzero(first)[0]
+    v = np.add.reduceat(v, starts) if len(starts) else v[:0]
+    key = key[starts]
+    return np.stack([key // (N * N), (key // N) % N, key % N]).astype(np.int64), v
+
+
+def make_symmetric(idx, val, T, N):
+    """(A_t + A_t^T)/2 per slice (ref: read_data.py:88-109)."""
+    idx, val = np.asarray(idx, np.int64), np.asarray(val, np.float64)
+    return _coalesce(np.concatenate([idx[0], idx[0]]), np.concatenate([idx[1], idx[2]]),
+                     np.concatenate([idx[2], idx[1]]), np.concatenate([val, val]) / 2, N)
+
+
+def edge_life(idx, val, T, N, window):
+    """A_new[t] = sum_{s=max(0,t-w+1)}^{t} A[s] (ref: read_data.py:116-125)."""
+    idx, val = np.asarray(idx, np.int64), np.asarray(val, np.float64)
+    ts, rs, cs, vs = [], [], [], []
+    for t in range(T):
+        sel = (idx[0] >= max(0, t - window + 1)) & (idx[0] <= t)
+        ts.append(np.full(int(sel.sum()), t, np.int64))
+        rs.append(idx[1, sel])
+        cs.append(idx[2, sel])
+        vs.append(val[sel])
+    return _coalesce(np.concatenate(ts), np.concatenate(rs), np.concatenate(cs), np.concatenate(vs), N)
+
+
+def laplacian_transformation(idx, val, T, N):
+    """D^-1/2 (B + I) D^-1/2 per slice, D = row sums of B + I (ref: read_data.py:130-164)."""
+    idx, val = np.asarray(idx, np.int64), np.asarray(val, np.float64)
+    t = np.concatenate([idx[0], np.repeat(np.arange(T), N)])
+    r = np.concatenate([idx[1], np.tile(np.arange(N), T)])
+    c = np.concatenate([idx[2], np.tile(np.arange(N), T)])
+    v = np.concatenate([val, np.ones(T * N)])
+    ci, cv = _coalesce(t, r, c, v, N)
+    deg = np.zeros(T * N)
+    np.add.at(deg, ci[0] * N + ci[1], cv)
+    d = 1.0 / np.sqrt(deg)
+    return ci, cv * d[ci[0] * N + ci[1]] * d[ci[0] * N + ci[2]]
+
+
+def create_sparse(idx, val, start, end):
+    """time window [start, end), re-based (ref: read_data.py:174-183)."""
+    idx, val = np.asarray(idx, np.int64), np.asarray(val, np.float64)
+    sel = (idx[0] >= start) & (idx[0] < end)
+    out = idx[:, sel].copy()
+    out[0] -= start
+    return out, val[sel]

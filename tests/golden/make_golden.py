@@ -255,7 +255,38 @@ def gen_models():
     print("models.npz", len(d))
 
 
+def gen_preprocess():
+    """read_data.py:88-188 helper functions executed from the reference text on a small random tensor."""
+    src = open(os.path.join(REF, "read_data.py")).read().split("\n")
+
+    def grab(name):
+        a = [i for i, l in enumerate(src) if l.startswith("def " + name + "(")][0]
+        b = a + 1
+        while b < len(src) and (src[b].startswith((" ", "\t")) or src[b].strip() == ""):
+            b += 1
+        return "\n".join(src[a:b])
+    ns = {"torch": t, "np": np, "edge_life_window": 3}
+    for f in ("func_make_symmetric", "func_edge_life", "func_laplacian_transformation", "func_create_sparse"):
+        exec(grab(f), ns)
+    TT, N = 7, 30
+    g = t.Generator().manual_seed(21)
+    n = 260
+    idx = t.stack([t.randint(0, TT, (n,), generator=g), t.randint(0, N, (n,), generator=g),
+                   t.randint(0, N, (n,), generator=g)])
+    A = t.sparse.DoubleTensor(idx, t.ones(n, dtype=t.double), t.Size([TT, N, N])).coalesce()
+    B = ns["func_make_symmetric"](A, N, TT)
+    E = ns["func_edge_life"](B, N, TT)
+    C = ns["func_laplacian_transformation"](E, N, TT)
+    S = ns["func_create_sparse"](C, N, TT, 4, 2, 6)
+    d = {"TT_N_w": np.array([TT, N, 3])}
+    for name, x in (("A", A), ("sym", B), ("life", E), ("lap", C), ("win", S)):
+        d[name + "_idx"], d[name + "_val"] = x._indices().numpy(), x._values().numpy()
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **d)
+    print("preprocess.npz", {k: v.shape for k, v in d.items() if k.endswith("_idx")})
+
+
 if __name__ == "__main__":
+    gen_preprocess()
     gen_mproduct()
     gen_chess()
     gen_models()

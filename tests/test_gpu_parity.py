@@ -577,3 +577,52 @@ def test_layer_step_matches_autograd_and_sharding(tg, act, mode):
     assert relerr(total, Hd.grad) <= TOL_GRAD
     assert relerr(dW_lo + dW_hi, layer.W.grad) <= TOL_GRAD
     assert relerr(dU_lo + dU_hi, layer.U.grad) <= TOL_GRAD
+
+
+# --------------------------------------------------------------------------
+# graph preparation (ref: read_data.py:88-188)
+# --------------------------------------------------------------------------
+def test_graph_preparation_golden_and_oracle(tg):
+    import os
+    from conftest import GOLDEN
+    from tmgcn_b200 import preprocess as pp
+    g = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    TT, N, w = (int(x) for x in g["TT_N_w"])
+
+    def coo(name):
+        return torch.sparse_coo_tensor(torch.from_numpy(g[name + "_idx"]), torch.from_numpy(g[name + "_val"]),
+                                       (TT, N, N)).coalesce()
+
+    def same(x, name, rtol):
+        assert x.is_coalesced() and x.dtype == torch.float64
+        assert torch.equal(x._indices().cpu(), torch.from_numpy(g[name + "_idx"]))
+        np.testing.assert_allclose(x._values().cpu().numpy(), g[name + "_val"], rtol=rtol, atol=0)
+    B = pp.func_make_symmetric(coo("A"), N, TT)
+    same(B, "sym", 1e-15)
+    E = pp.func_edge_life(B, N, TT, edge_life_window=w)
+    same(E, "life", 1e-15)
+    C = pp.func_laplacian_transformation(E, N, TT)
+    same(C, "lap", 1e-14)
+    S = pp.func_create_sparse(C, N, TT, 4, 2, 6)
+    assert tuple(S.shape) == (4, N, N)
+    assert torch.equal(S._indices().cpu(), torch.from_numpy(g["win_idx"]))
+    np.testing.assert_allclose(S._values().cpu().numpy(), g["win_val"], rtol=1e-14, atol=0)
+    # a bigger unsymmetric random tensor with self loops, duplicates and empty slices against the oracle
+    T2, N2 = 9, 2500
+    gen = torch.Generator().manual_seed(4)
+    n = 60000
+    idx = torch.stack([torch.randint(1, T2 - 1, (n,), generator=gen), torch.randint(0, N2, (n,), generator=gen),
+                       torch.randint(0, N2, (n,), generator=gen)])
+    A2 = torch.sparse_coo_tensor(idx, torch.ones(n, dtype=torch.float64), (T2, N2, N2)).coalesce()
+    ai, av = A2._indices().numpy(), A2._values().numpy()
+    si, sv = oracle.make_symmetric(ai, av, T2, N2)
+    li, lv = oracle.edge_life(si, sv, T2, N2, 4)
+    ci, cv = oracle.laplacian_transformation(li, lv, T2, N2)
+    out = pp.func_laplacian_transformation(pp.func_edge_life(pp.func_make_symmetric(A2, N2, T2), N2, T2, 4), N2, T2)
+    assert torch.equal(out._indices().cpu(), torch.from_numpy(ci))
+    np.testing.assert_allclose(out._values().cpu().numpy(), cv, rtol=1e-13, atol=0)
+    # the synthetic-input generator's preparation (symmetrise + I + normalise) is the same pipeline
+    ni, nv = oracle.normalise_adjacency(ai, av, T2, N2)
+    out2 = pp.func_laplacian_transformation(pp.func_make_symmetric(A2, N2, T2), N2, T2)
+    assert torch.equal(out2._indices().cpu(), torch.from_numpy(ni))
+    np.testing.assert_allclose(out2._values().cpu().numpy(), nv, rtol=1e-13, atol=0)

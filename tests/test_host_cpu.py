@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib.tmgcn_last_error(), bytes)
     # size queries are host-only and safe without a GPU
     assert lib.tmgcn_scan_ws_bytes(10_000) >= 8
-    assert lib.tmgcn_csr_transpose_ws_bytes(10, 100) == 100 * 8 + 10 * 8
+    assert lib.tmgcn_csr_transpose_ws_bytes(10, 100, 0) == 100 * 8 + 10 * 8
+    assert lib.tmgcn_csr_transpose_ws_bytes(10, 100, 1) == 100 * 16 + 10 * 8
 
 
 def test_product_fails_loudly_without_gpu():

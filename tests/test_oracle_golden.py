@@ -140,3 +140,19 @@ def test_normalise_adjacency_small():
     np.testing.assert_allclose(got, ref, rtol=1e-14)
     key = (idx[0] * N + idx[1]) * N + idx[2]
     assert np.all(np.diff(key) > 0)
+
+
+def test_graph_preparation_matches_reference():
+    """oracle restatement of read_data.py:88-188 against the reference functions' own outputs."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    TT, N, w = (int(x) for x in g["TT_N_w"])
+    si, sv = oracle.make_symmetric(g["A_idx"], g["A_val"], TT, N)
+    assert np.array_equal(si, g["sym_idx"]) and np.allclose(sv, g["sym_val"], rtol=1e-15, atol=0)
+    li, lv = oracle.edge_life(si, sv, TT, N, w)
+    assert np.array_equal(li, g["life_idx"]) and np.allclose(lv, g["life_val"], rtol=1e-15, atol=0)
+    ci, cv = oracle.laplacian_transformation(li, lv, TT, N)
+    assert np.array_equal(ci, g["lap_idx"]) and np.allclose(cv, g["lap_val"], rtol=1e-14, atol=0)
+    wi, wv = oracle.create_sparse(ci, cv, 2, 6)
+    assert np.array_equal(wi, g["win_idx"]) and np.allclose(wv, g["win_val"], rtol=1e-14, atol=0)

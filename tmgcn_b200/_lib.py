@@ -26,9 +26,13 @@ PROTOTYPES = {
     "tmgcn_rowptr_from_sorted_rows": (_i, [_p, _l, _l, _p, _p]),
     "tmgcn_mtransform_sparse_plan": (_i, [_p, _p, _i, _i, _l, _p, _i, _p, _p]),
     "tmgcn_mtransform_sparse_run": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _p, _p, _p, _i, _p]),
-    "tmgcn_csr_transpose_ws_bytes": (_z, [_l, _l]),
+    "tmgcn_csr_transpose_ws_bytes": (_z, [_l, _l, _i]),
     "tmgcn_csr_transpose_plan": (_i, [_p, _p, _i, _l, _p, _p]),
-    "tmgcn_csr_transpose_run": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _p, _p]),
+    "tmgcn_csr_transpose_run": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _i, _p, _p]),
+    "tmgcn_csr_axpby_plan": (_i, [_p, _p, _p, _p, _l, _p, _p]),
+    "tmgcn_csr_axpby_run": (_i, [_p, _p, _p, _p, _p, _p, C.c_double, C.c_double, _l, _p, _p, _p, _i, _p]),
+    "tmgcn_csr_row_sums": (_i, [_p, _p, _l, _p, _i, _p]),
+    "tmgcn_csr_scale_sym": (_i, [_p, _p, _p, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_fwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_bwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_fwd_split": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _p]),

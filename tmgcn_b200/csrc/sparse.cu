@@ -221,14 +221,16 @@ __global__ void transpose_count(const int64_t *__restrict__ rowptr, const int32_
     }
 }
 
-struct __align__(8) RowVal {
+template <typename VT>
+struct RowVal {
+    VT val;
     int32_t row;
-    float val;
 };
 
+template <typename VT>
 __global__ void transpose_fill(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                               const float *__restrict__ val, int64_t N, int64_t n_rows,
-                               unsigned long long *__restrict__ cursor, RowVal *__restrict__ tmp) {
+                               const VT *__restrict__ val, int64_t N, int64_t n_rows,
+                               unsigned long long *__restrict__ cursor, RowVal<VT> *__restrict__ tmp) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
@@ -238,7 +240,7 @@ __global__ void transpose_fill(const int64_t *__restrict__ rowptr, const int32_t
         const int64_t s = rowptr[row], e = rowptr[row + 1];
         for (int64_t k = s + lane; k < e; k += 32) {
             unsigned long long pos = atomicAdd(&cursor[tbase + col[k]], 1ULL);
-            RowVal rv;
+            RowVal<VT> rv;
             rv.row = i;
             rv.val = val[k];
             tmp[pos] = rv;
@@ -248,17 +250,18 @@ __global__ void transpose_fill(const int64_t *__restrict__ rowptr, const int32_t
 
 // rank sort of every transposed row (keys are unique inside a row): restores
 // ascending order so the backward SpMM sums in a reproducible order.
-__global__ void transpose_rank_sort(const int64_t *__restrict__ t_rowptr, const RowVal *__restrict__ tmp,
-                                    int64_t n_rows, int32_t *__restrict__ t_col, float *__restrict__ t_val) {
+template <typename VT>
+__global__ void transpose_rank_sort(const int64_t *__restrict__ t_rowptr, const RowVal<VT> *__restrict__ tmp,
+                                    int64_t n_rows, int32_t *__restrict__ t_col, VT *__restrict__ t_val) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < n_rows; row += warps_total) {
         const int64_t s = t_rowptr[row], e = t_rowptr[row + 1];
         const int64_t len = e - s;
         if (len <= 32) {
-            RowVal mine;
+            RowVal<VT> mine;
             mine.row = INT_MAX;
-            mine.val = 0.f;
+            mine.val = 0;
             if (lane < len) mine = tmp[s + lane];
             int rank = 0;
             for (int j = 0; j < (int)len; ++j) {
@@ -271,7 +274,7 @@ __global__ void transpose_rank_sort(const int64_t *__restrict__ t_rowptr, const 
             }
         } else {
             for (int64_t a = lane; a < len; a += 32) {
-                RowVal mine = tmp[s + a];
+                RowVal<VT> mine = tmp[s + a];
                 int64_t rank = 0;
                 for (int64_t j = 0; j < len; ++j) rank += tmp[s + j].row < mine.row;
                 t_col[s + rank] = mine.row;
@@ -279,6 +282,61 @@ __global__ void transpose_rank_sort(const int64_t *__restrict__ t_rowptr, const 
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------
+// graph preparation (ref: read_data.py:88-164): C = alpha*A + beta*B by a 2-way sorted row merge,
+// row sums and the symmetric degree scaling D^-1/2 (.) D^-1/2.  Thread per row.
+// ------------------------------------------------------------------------
+template <bool COUNT_ONLY, typename VT>
+__global__ void csr_axpby_kernel(const int64_t *__restrict__ arow, const int32_t *__restrict__ acol,
+                                 const VT *__restrict__ aval, const int64_t *__restrict__ brow,
+                                 const int32_t *__restrict__ bcol, const VT *__restrict__ bval, double alpha,
+                                 double beta, int64_t n_rows, int64_t *__restrict__ counts,
+                                 const int64_t *__restrict__ crow, int32_t *__restrict__ ccol,
+                                 VT *__restrict__ cval) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    int64_t pa = arow[row], ea = arow[row + 1], pb = brow[row], eb = brow[row + 1];
+    int64_t o = COUNT_ONLY ? 0 : crow[row], n = 0;
+    while (pa < ea || pb < eb) {
+        const int ca = pa < ea ? acol[pa] : INT_MAX, cb = pb < eb ? bcol[pb] : INT_MAX;
+        const int m = min(ca, cb);
+        if (!COUNT_ONLY) {
+            double v = 0.0;
+            if (ca == m) v += alpha * (double)aval[pa];
+            if (cb == m) v += beta * (double)bval[pb];
+            ccol[o + n] = m;
+            cval[o + n] = (VT)v;
+        }
+        pa += ca == m;
+        pb += cb == m;
+        ++n;
+    }
+    if (COUNT_ONLY) counts[row] = n;
+}
+
+template <typename VT>
+__global__ void csr_row_sums_kernel(const int64_t *__restrict__ rowptr, const VT *__restrict__ val, int64_t n_rows,
+                                    double *__restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double s = 0.0;
+    for (int64_t k = rowptr[row]; k < rowptr[row + 1]; ++k) s += (double)val[k];
+    out[row] = s;
+}
+
+// val[k] <- val[k] * deg[row]^-1/2 * deg[t*N + col[k]]^-1/2   (ref: read_data.py:143-159)
+template <typename VT>
+__global__ void csr_scale_sym_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                     VT *__restrict__ val, int64_t N, int64_t n_rows,
+                                     const double *__restrict__ deg) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int64_t tbase = (row / N) * N;
+    const double di = 1.0 / sqrt(deg[row]);
+    for (int64_t k = rowptr[row]; k < rowptr[row + 1]; ++k)
+        val[k] = (VT)(((double)val[k] * di) * (1.0 / sqrt(deg[tbase + col[k]])));
 }
 
 static int grid_for_warps(int64_t n_warps, int threads) {
@@ -353,8 +411,64 @@ int tmgcn_mtransform_sparse_run(const int64_t *in_rowptr, const int32_t *in_col,
                                       out_rowptr, out_col, (float *)out_val, (cudaStream_t)stream);
 }
 
-size_t tmgcn_csr_transpose_ws_bytes(int64_t n_rows, int64_t nnz) {
-    return (size_t)nnz * sizeof(RowVal) + (size_t)n_rows * sizeof(int64_t);
+int tmgcn_csr_axpby_plan(const int64_t *a_rowptr, const int32_t *a_col, const int64_t *b_rowptr, const int32_t *b_col,
+                         int64_t n_rows, int64_t *counts, void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0, "csr_axpby_plan: bad sizes");
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(a_rowptr && b_rowptr && counts, "csr_axpby_plan: null pointer");
+    csr_axpby_kernel<true, float><<<(unsigned)ceil_div(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(
+        a_rowptr, a_col, nullptr, b_rowptr, b_col, nullptr, 0.0, 0.0, n_rows, counts, nullptr, nullptr, nullptr);
+    return after_launch("csr_axpby<count>");
+}
+
+int tmgcn_csr_axpby_run(const int64_t *a_rowptr, const int32_t *a_col, const void *a_val, const int64_t *b_rowptr,
+                        const int32_t *b_col, const void *b_val, double alpha, double beta, int64_t n_rows,
+                        const int64_t *c_rowptr, int32_t *c_col, void *c_val, int val_is_f64, void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0, "csr_axpby_run: bad sizes");
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(a_rowptr && b_rowptr && c_rowptr, "csr_axpby_run: null pointer");
+    const unsigned grid = (unsigned)ceil_div(n_rows, 128);
+    if (val_is_f64)
+        csr_axpby_kernel<false, double><<<grid, 128, 0, (cudaStream_t)stream>>>(
+            a_rowptr, a_col, (const double *)a_val, b_rowptr, b_col, (const double *)b_val, alpha, beta, n_rows,
+            nullptr, c_rowptr, c_col, (double *)c_val);
+    else
+        csr_axpby_kernel<false, float><<<grid, 128, 0, (cudaStream_t)stream>>>(
+            a_rowptr, a_col, (const float *)a_val, b_rowptr, b_col, (const float *)b_val, alpha, beta, n_rows, nullptr,
+            c_rowptr, c_col, (float *)c_val);
+    return after_launch("csr_axpby<fill>");
+}
+
+int tmgcn_csr_row_sums(const int64_t *rowptr, const void *val, int64_t n_rows, double *out, int val_is_f64,
+                       void *stream) {
+    TMGCN_REQUIRE(n_rows >= 0, "csr_row_sums: bad sizes");
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(rowptr && out, "csr_row_sums: null pointer");
+    const unsigned grid = (unsigned)ceil_div(n_rows, 256);
+    if (val_is_f64)
+        csr_row_sums_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, (const double *)val, n_rows, out);
+    else
+        csr_row_sums_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, (const float *)val, n_rows, out);
+    return after_launch("csr_row_sums");
+}
+
+int tmgcn_csr_scale_sym(const int64_t *rowptr, const int32_t *col, void *val, int T, int64_t N, const double *deg,
+                        int val_is_f64, void *stream) {
+    const int64_t n_rows = (int64_t)T * N;
+    TMGCN_REQUIRE(T >= 0 && N >= 0, "csr_scale_sym: bad sizes");
+    if (n_rows == 0) return 0;
+    TMGCN_REQUIRE(rowptr && deg, "csr_scale_sym: null pointer");
+    const unsigned grid = (unsigned)ceil_div(n_rows, 256);
+    if (val_is_f64)
+        csr_scale_sym_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, (double *)val, N, n_rows, deg);
+    else
+        csr_scale_sym_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(rowptr, col, (float *)val, N, n_rows, deg);
+    return after_launch("csr_scale_sym");
+}
+
+size_t tmgcn_csr_transpose_ws_bytes(int64_t n_rows, int64_t nnz, int val_is_f64) {
+    return (size_t)nnz * (val_is_f64 ? sizeof(RowVal<double>) : sizeof(RowVal<float>)) +
+           (size_t)n_rows * sizeof(int64_t);
 }
 
 int tmgcn_csr_transpose_plan(const int64_t *rowptr, const int32_t *col, int T, int64_t N, int64_t *counts,
@@ -370,20 +484,31 @@ int tmgcn_csr_transpose_plan(const int64_t *rowptr, const int32_t *col, int T, i
     return after_launch("transpose_count");
 }
 
-int tmgcn_csr_transpose_run(const int64_t *rowptr, const int32_t *col, const float *val, int T, int64_t N,
-                            const int64_t *t_rowptr, int32_t *t_col, float *t_val, void *ws, void *stream) {
+int tmgcn_csr_transpose_run(const int64_t *rowptr, const int32_t *col, const void *val, int T, int64_t N,
+                            const int64_t *t_rowptr, int32_t *t_col, void *t_val, int val_is_f64, void *ws,
+                            void *stream) {
     const int64_t n_rows = (int64_t)T * N;
     if (n_rows == 0) return 0;
     TMGCN_REQUIRE(rowptr && t_rowptr && ws, "csr_transpose_run: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *cursor = (unsigned long long *)ws;
-    RowVal *tmp = (RowVal *)((char *)ws + (size_t)n_rows * sizeof(int64_t));
+    void *tmp = (char *)ws + (size_t)n_rows * sizeof(int64_t);
     TMGCN_CUDA(cudaMemcpyAsync(cursor, t_rowptr, (size_t)n_rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     const int threads = 256;
     const int grid = grid_for_warps(n_rows, threads);
-    transpose_fill<<<grid, threads, 0, st>>>(rowptr, col, val, N, n_rows, cursor, tmp);
-    if (after_launch("transpose_fill")) return 1;
-    transpose_rank_sort<<<grid, threads, 0, st>>>(t_rowptr, tmp, n_rows, t_col, t_val);
+    if (val_is_f64) {
+        transpose_fill<double><<<grid, threads, 0, st>>>(rowptr, col, (const double *)val, N, n_rows, cursor,
+                                                         (RowVal<double> *)tmp);
+        if (after_launch("transpose_fill")) return 1;
+        transpose_rank_sort<double><<<grid, threads, 0, st>>>(t_rowptr, (const RowVal<double> *)tmp, n_rows, t_col,
+                                                              (double *)t_val);
+    } else {
+        transpose_fill<float><<<grid, threads, 0, st>>>(rowptr, col, (const float *)val, N, n_rows, cursor,
+                                                        (RowVal<float> *)tmp);
+        if (after_launch("transpose_fill")) return 1;
+        transpose_rank_sort<float><<<grid, threads, 0, st>>>(t_rowptr, (const RowVal<float> *)tmp, n_rows, t_col,
+                                                             (float *)t_val);
+    }
     return after_launch("transpose_rank_sort");
 }
 

@@ -124,8 +124,7 @@ class SliceCSR:
         """Per-slice transpose (cached) for the backward SpMM."""
         if self._t is not None:
             return self._t
-        if self.val.dtype != torch.float32:
-            raise TypeError("transpose: fp32 values only")
+        f64 = 1 if self.val.dtype == torch.float64 else 0
         lib = _lib.load()
         dev = self.rowptr.device
         n_rows = self.T * self.N
@@ -134,10 +133,10 @@ class SliceCSR:
         t_rowptr = exclusive_scan(counts)
         del counts
         t_col = torch.empty(self.nnz, dtype=torch.int32, device=dev)
-        t_val = torch.empty(self.nnz, dtype=torch.float32, device=dev)
-        ws = _ws(lib.tmgcn_csr_transpose_ws_bytes(n_rows, self.nnz))
+        t_val = torch.empty(self.nnz, dtype=self.val.dtype, device=dev)
+        ws = _ws(lib.tmgcn_csr_transpose_ws_bytes(n_rows, self.nnz, f64))
         _lib.check(lib.tmgcn_csr_transpose_run(_p(self.rowptr), _p(self.col), _p(self.val), self.T, self.N,
-                                               _p(t_rowptr), _p(t_col), _p(t_val), _p(ws), _stream()))
+                                               _p(t_rowptr), _p(t_col), _p(t_val), f64, _p(ws), _stream()))
         self._t = SliceCSR(self.T, self.N, t_rowptr, t_col, t_val)
         self._t._t = self
         return self._t
