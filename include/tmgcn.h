@@ -124,6 +124,14 @@ int tmgcn_mtransform_dense_fwd_split(const float *x_halo, const float *x_own, fl
 int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                      const float *band_w, int b, int s_begin, int s_end, void *stream);
 
+/* inverse transform  Y = inv(M) x_3 Z  (ref: Minv = inv(M), ehf:183-184; applied at ehf:223-224, 331-332,
+ * 338-341): inv(M) of a banded M is dense, so it is applied as the banded substitution M x_3 Y = Z marching
+ * through time (fp64 recurrence, fp32 in/out); _bwd solves with M^T (the adjoint).  Unsharded only (halo = 0). */
+int tmgcn_mtransform_dense_solve_fwd(const float *z, float *y, int T, int64_t NF, const float *band_w, int b,
+                                     void *stream);
+int tmgcn_mtransform_dense_solve_bwd(const float *g_y, float *g_z, int T, int64_t NF, const float *band_w, int b,
+                                     void *stream);
+
 /* ---- (d) facewise SpMM  P_t = A~_t . X_t -----------------------------------
  * ref: the loop ehf:205-207 / ehf:309-311 and compute_AX ehf:301-305, 469-473.
  * y[t, i, :] = act( sum_k val[k] * x[t, col[k], :] ), all T slices in one launch.

@@ -20,6 +20,7 @@ __all__ = [
     "compute_AtXt",
     "flat_edge_ids",
     "nonlin",
+    "apply_Minv",
     "OracleGCN",
     "OracleGCN2",
     "OracleKWGCN",
@@ -199,11 +200,20 @@ def _readout(Y, src, trg, U):
 # a12. module restatements (use_Minv=False, condensed_W=True: the setting of
 # every shipped experiment, e.g. experiment_bitcoin_our.py:109)
 # --------------------------------------------------------------------------
+def apply_Minv(M, Z):
+    """Y = inv(M) @ Z.reshape(T, -1) (ref: ehf:183-184, 223-224).  The reference multiplies its fp64 inv(M)
+    with the fp32 buffer and raises a dtype error on the shipped dtypes [probed]; the only reading that runs is
+    "promote to fp64, round the result back to fp32", which is what this does.  PARITY UNPINNED for this flag."""
+    Minv = torch.from_numpy(np.linalg.inv(M.numpy()))
+    return torch.matmul(Minv, Z.double().reshape(Z.shape[0], -1)).reshape(Z.size()).float()
+
+
 class OracleGCN(torch.nn.Module):
     """1-layer TM-GCN (ref: ehf:156-234)."""
 
-    def __init__(self, At, X, edges, M, W, U, as_reference=True):
+    def __init__(self, At, X, edges, M, W, U, as_reference=True, use_Minv=False):
         super().__init__()
+        self.use_Minv = use_Minv
         self.M, self.N, self.as_reference = M, X.shape[1], as_reference
         self.W = torch.nn.Parameter(W.clone())
         self.U = torch.nn.Parameter(U.clone())
@@ -217,6 +227,8 @@ class OracleGCN(torch.nn.Module):
         else:
             AtXt, src, trg = self.AtXt, self.src, self.trg
         Y = torch.matmul(AtXt, self.W)  # ehf:222
+        if self.use_Minv:
+            Y = apply_Minv(self.M, Y)  # ehf:223-224
         return _readout(Y, src, trg, self.U)
 
 
@@ -224,8 +236,9 @@ class OracleGCN2(torch.nn.Module):
     """2-layer TM-GCN (ref: ehf:236-357), use_Minv=False."""
 
     def __init__(self, At, X, edges, M, W1, W2, U, apply_M_twice=False,
-                 apply_M_three_times=False, nonlin2="relu", as_reference=True):
+                 apply_M_three_times=False, nonlin2="relu", as_reference=True, use_Minv=False):
         super().__init__()
+        self.use_Minv = use_Minv
         self.At, self.M, self.N = At, M, X.shape[1]
         self.apply_M_twice, self.apply_M_three_times = apply_M_twice, apply_M_three_times
         self.as_reference = as_reference
@@ -242,6 +255,11 @@ class OracleGCN2(torch.nn.Module):
             src, trg = flat_edge_ids(edges, self.N)
         else:
             AtXt, src, trg = self.AtXt, self.src, self.trg
+        if self.use_Minv:  # ehf:331-341
+            Y = self.f(apply_Minv(self.M, torch.matmul(AtXt, self.W1))).double()
+            AtYt = compute_AtXt(self.At, Y, self.M, self.as_reference)
+            Z = apply_Minv(self.M, torch.matmul(AtYt, self.W2))
+            return _readout(Z, src, trg, self.U)
         Y = self.f(torch.matmul(AtXt, self.W1)).double()  # ehf:330-335
         if self.apply_M_twice:  # ehf:342-346
             Z = torch.matmul(compute_AtXt(self.At, Y, self.M, self.as_reference), self.W2)

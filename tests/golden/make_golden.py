@@ -251,6 +251,9 @@ def gen_models():
         p_.grad = None
     out.backward(dReg)
     d["reg_dW"], d["reg_dlw"], d["reg_dlb"] = m.W.grad.numpy().copy(), m.lin1.weight.grad.numpy().copy(), m.lin1.bias.grad.numpy().copy()
+    # use_Minv=True (ehf:183-184, 223-224) cannot be pinned here: the reference itself raises
+    # "expected m1 and m2 to have the same dtype, but got: double != float" at ehf:224 (fp64 inv(M) times the
+    # fp32 AtXt buffer) on the shipped dtypes, so that flag is checked against the dense-inverse formula instead.
     np.savez_compressed(os.path.join(OUT, "models.npz"), **d)
     print("models.npz", len(d))
 

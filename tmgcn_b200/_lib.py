@@ -35,6 +35,8 @@ PROTOTYPES = {
     "tmgcn_csr_scale_sym": (_i, [_p, _p, _p, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_fwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_bwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
+    "tmgcn_mtransform_dense_solve_fwd": (_i, [_p, _p, _i, _l, _p, _i, _p]),
+    "tmgcn_mtransform_dense_solve_bwd": (_i, [_p, _p, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_fwd_split": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_bwd_range": (_i, [_p, _p, _i, _i, _l, _p, _i, _i, _i, _p]),
     "tmgcn_spmm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _l, _i, _i, _p]),

@@ -133,6 +133,72 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
     }
 }
 
+// ---- inverse M-transform  Y = inv(M) x_3 Z  as a banded substitution (ref: ehf:183-184, 223-224) -----------
+// The reference multiplies by the dense T x T matrix inv(M).  M is banded lower triangular, so inv(M) x_3 Z is
+// the solution of M x_3 Y = Z:  y[t] = (z[t] - sum_{i>=1} M[t,t-i] y[t-i]) / M[t,t]  -- the same time march
+// as the forward stencil with the ring holding previous OUTPUTS (an IIR filter).  The recurrence runs in
+// fp64 registers (loads / stores fp32) so the feedback does not amplify rounding over hundreds of slices.
+// TRANSPOSED solves M^T x_3 g_in = g_out (the adjoint), marching downwards:
+//   g_in[s] = (g_out[s] - sum_{i>=1} M[s+i, s] g_in[s+i]) / M[s,s].
+template <int B, bool TRANSPOSED>
+__global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ src, float *__restrict__ dst, int T,
+                                                    int64_t n, const float *__restrict__ band_w, int b) {
+    extern __shared__ float sw[];
+    load_weights<B>(sw, band_w, T, b);
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    double ring[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) ring[k] = 0.0;
+    for (int u0 = 0; u0 < T; u0 += B) {
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int u = u0 + k;
+            if (u < T) {
+                const int t = TRANSPOSED ? T - 1 - u : u;
+                double acc = (double)__ldg(src + (int64_t)t * n + pos);
+#pragma unroll
+                for (int i = 1; i < B; ++i) {
+                    // forward: M[t, t-i] = sw[(t+B)*B + i];  transposed: M[t+i, t] = sw[(t+i+B)*B + i]
+                    const float w = TRANSPOSED ? sw[(t + i + B) * B + i] : sw[(t + B) * B + i];
+                    acc -= (double)w * ring[(k - i + 2 * B) % B];
+                }
+                acc /= (double)sw[(t + B) * B];
+                ring[k] = acc;
+                dst[(int64_t)t * n + pos] = (float)acc;
+            }
+        }
+    }
+}
+
+template <bool TRANSPOSED>
+static int solve_entry(const float *z, float *y, int T, int64_t NF, const float *band_w, int b, void *stream) {
+    TMGCN_REQUIRE(T >= 0 && NF >= 0, "mtransform_dense_solve: negative size");
+    TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform_dense_solve: band width b=%d outside [1, 32]", b);
+    if (NF == 0 || T == 0) return 0;
+    TMGCN_REQUIRE(z && y && band_w, "mtransform_dense_solve: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+#define TMGCN_SOLVE(BB)                                                                                     \
+    if (b <= BB) {                                                                                          \
+        const size_t smem = (size_t)(T + 2 * BB) * BB * sizeof(float);                                      \
+        TMGCN_REQUIRE(smem <= 200 * 1024, "mtransform_dense_solve: T=%d too large for the weight table", T); \
+        auto kern = solve_kernel<BB, TRANSPOSED>;                                                           \
+        if (smem > 48 * 1024)                                                                               \
+            TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<(unsigned)ceil_div(NF, 256), 256, smem, st>>>(z, y, T, NF, band_w, b);                       \
+        return after_launch(TRANSPOSED ? "solve_bwd" : "solve_fwd");                                        \
+    }
+    TMGCN_SOLVE(2)
+    TMGCN_SOLVE(4)
+    TMGCN_SOLVE(8)
+    TMGCN_SOLVE(12)
+    TMGCN_SOLVE(16)
+    TMGCN_SOLVE(20)
+    TMGCN_SOLVE(32)
+#undef TMGCN_SOLVE
+    return 1;
+}
+
 template <int B, int V, bool REVERSE>
 static int launch_stencil(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
                           const float *band_w, int b, int s_begin, int s_end, cudaStream_t st) {
@@ -205,6 +271,14 @@ int tmgcn_mtransform_dense_fwd_split(const float *x_halo, const float *x_own, fl
 int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream) {
     return tmgcn::stencil_entry<true>(g_out, g_out, g_in, T_out, halo, NF, band_w, b, 0, halo + T_out, stream);
+}
+int tmgcn_mtransform_dense_solve_fwd(const float *z, float *y, int T, int64_t NF, const float *band_w, int b,
+                                     void *stream) {
+    return tmgcn::solve_entry<false>(z, y, T, NF, band_w, b, stream);
+}
+int tmgcn_mtransform_dense_solve_bwd(const float *g_y, float *g_z, int T, int64_t NF, const float *band_w, int b,
+                                     void *stream) {
+    return tmgcn::solve_entry<true>(g_y, g_z, T, NF, band_w, b, stream);
 }
 int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                      const float *band_w, int b, int s_begin, int s_end, void *stream) {

@@ -6,9 +6,9 @@ create_matrix_M helpers -- backed by libtmgcn_b200.so instead of ATen CPU ops.
 
 Differences a caller can observe (all documented in INTEGRATION.md):
   * results and parameters live on the current CUDA device (fp32);
-  * `use_Minv=True` raises NotImplementedError (no shipped experiment uses it; SURVEY.md
-    section 8f lists it as a "next" row); `condensed_W=False` (per-slice weights) runs one GEMM
-    launch per slice.
+  * `use_Minv=True` applies inv(M) as a banded substitution in time (M x_3 Y = Z) instead of a dense
+    T x T product; `condensed_W=False` (per-slice weights) runs one GEMM launch per slice.  Both
+    take the general (dense-gradient) backward.
 """
 from __future__ import annotations
 
@@ -115,8 +115,6 @@ class EmbeddingGCN(_Base):
 
     def __init__(self, At, X, edges, M, hidden_feat=[2, 2], condensed_W=False, use_Minv=True):
         super().__init__()
-        if use_Minv:
-            raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
         self.M = M
         self.band = Band(M)
         self.use_Minv = use_Minv
@@ -144,8 +142,11 @@ class EmbeddingGCN(_Base):
             plan = EdgePlan(edges, self.N)
         else:
             AtXt, plan = self.AtXt, self.edge_plan
-        if not self.condensed_W:                              # per-slice weights: batched matmul (ehf:222)
-            return ops.edge_readout(ops.gemm_xw_sliced(AtXt, self.W), self.U, plan)
+        if self.use_Minv or not self.condensed_W:             # general path (ehf:222-232)
+            Y = ops.gemm_xw(AtXt, self.W) if self.condensed_W else ops.gemm_xw_sliced(AtXt, self.W)
+            if self.use_Minv:                                 # Y = inv(M) x_3 (AtXt W), ehf:223-224
+                Y = ops.mtransform_dense_inv(Y, self.band)
+            return ops.edge_readout(Y, self.U, plan)
         # ref: ehf:222 (GEMM) + ehf:228-232 (readout): a linear map followed by a C-class readout
         return ops.propagate_linear_readout(AtXt, self.W, self.U, None, None, plan)
 
@@ -156,8 +157,6 @@ class EmbeddingGCN2(_Base):
     def __init__(self, At, X, edges, M, hidden_feat=[2, 2, 2], condensed_W=False, use_Minv=True,
                  apply_M_twice=False, apply_M_three_times=False, nonlin2="relu"):
         super().__init__()
-        if use_Minv:
-            raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
         self.condensed_W = condensed_W
         self.At = At
         self.M = M
@@ -199,10 +198,16 @@ class EmbeddingGCN2(_Base):
             plan = EdgePlan(edges, self.N)
         else:
             AtXt, plan = self.AtXt, self.edge_plan
-        if not self.condensed_W:                              # per-slice weights: batched matmuls
-            Y = ops.gemm_xw_sliced(AtXt, self.W1, self.nonlin2)
+        if self.use_Minv or not self.condensed_W:             # general path, ehf:330-349 branch by branch
+            mm = ops.gemm_xw if self.condensed_W else ops.gemm_xw_sliced
+            if self.use_Minv:                                 # ehf:331-332, 337-341
+                Y = ops.activation(ops.mtransform_dense_inv(mm(AtXt, self.W1), self.band), self.nonlin2)
+                AtYt = ops.spmm(self.At_csr, ops.mtransform_dense(Y, self.band))
+                Z = ops.mtransform_dense_inv(mm(AtYt, self.W2), self.band)
+                return ops.edge_readout(Z, self.U, plan)
+            Y = mm(AtXt, self.W1, self.nonlin2)
             Yt = ops.mtransform_dense(Y, self.band) if self.apply_M_twice else Y
-            Z = ops.gemm_xw_sliced(ops.spmm(self.At_csr, Yt), self.W2)
+            Z = mm(ops.spmm(self.At_csr, Yt), self.W2)
             if self.apply_M_twice and self.apply_M_three_times:
                 Z = ops.mtransform_dense(Z, self.band)
             return ops.edge_readout(Z, self.U, plan)
@@ -223,8 +228,6 @@ class EmbeddingGCN_reg(_Base):
 
     def __init__(self, At, X, M, hidden_feat=[2, 2], condensed_W=False, use_Minv=True):
         super().__init__()
-        if use_Minv:
-            raise NotImplementedError("use_Minv=True is outside the accelerated path (SURVEY.md section 8f)")
         self.M = M
         self.band = Band(M)
         self.use_Minv = use_Minv
@@ -243,6 +246,8 @@ class EmbeddingGCN_reg(_Base):
 
     def forward(self, At=None, X=None):
         Y = ops.gemm_xw(self.AtXt, self.W) if self.condensed_W else ops.gemm_xw_sliced(self.AtXt, self.W)
+        if self.use_Minv:                                                            # ehf:415-417
+            Y = ops.mtransform_dense_inv(Y, self.band)
         out = ops.gemm_xw(Y, self.lin1.weight.t().contiguous()) + self.lin1.bias     # (T, N, 1)
         return out.squeeze(2)
 

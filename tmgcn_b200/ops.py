@@ -328,6 +328,31 @@ class _Stencil(torch.autograd.Function):
         return stencil_bwd(g.contiguous(), band, t0, t1, halo), None, None, None, None
 
 
+class _Solve(torch.autograd.Function):
+    """Y = inv(M) x_3 Z by banded substitution; backward solves with M^T."""
+
+    @staticmethod
+    def forward(ctx, z, band):
+        lib = _lib.load()
+        z = z.contiguous()
+        y = torch.empty_like(z)
+        w = band.device_weights(0, band.T, torch.float32)
+        assert z.shape[0] == band.T
+        _lib.check(lib.tmgcn_mtransform_dense_solve_fwd(_p(z), _p(y), band.T, z[0].numel(), _p(w), band.b, _stream()))
+        ctx.band = band
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        band = ctx.band
+        g = g.contiguous()
+        gz = torch.empty_like(g)
+        w = band.device_weights(0, band.T, torch.float32)
+        _lib.check(lib.tmgcn_mtransform_dense_solve_bwd(_p(g), _p(gz), band.T, g[0].numel(), _p(w), band.b, _stream()))
+        return gz, None
+
+
 class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, csr, act):
@@ -521,6 +546,13 @@ def propagate_linear_readout(H, W, U, csr, band, plan):
 def mtransform_dense(x, band: Band, t0=0, t1=None, halo=0):
     """X~ = X x_3 M (ref: ehf:204), differentiable."""
     return _Stencil.apply(x, band, t0, t1, halo)
+
+
+def mtransform_dense_inv(z, band: Band):
+    """inv(M) x_3 Z (ref: ehf:223-224), differentiable; M banded lower triangular with a nonzero diagonal."""
+    if bool((band.w[:, 0] == 0).any()):
+        raise ValueError("M has a zero on its diagonal: not invertible")
+    return _Solve.apply(z, band)
 
 
 def spmm(csr: SliceCSR, x, act=None):
