@@ -127,6 +127,34 @@ def test_mtransform_sparse_vs_oracle(tg, T, N, m, rho, b, norm):
     np.testing.assert_allclose(torch.cat([v_lo, v_hi]).cpu().double().numpy(), ref_val, rtol=2e-7, atol=0)
 
 
+def test_mtransform_sparse_staged_variant_is_bit_identical(tg):
+    """the shared-memory staged merge kernel (TMGCN_MERGE_STAGED=1) against the default kernel, in a subprocess
+    because the choice is latched on first use; includes hub rows that overflow the staging capacity."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import tmgcn_b200 as tg
+from tmgcn_b200 import ops, synth
+T, N, b = 14, 3000, 10
+torch.manual_seed(11)
+idx, val = synth.synth_coo(N, T, 20000, 0.8, seed=3)
+hub = torch.stack([torch.randint(0, T, (6000,)), torch.full((6000,), 7), torch.randint(0, N, (6000,))])
+C = torch.sparse_coo_tensor(torch.cat([idx, hub], 1), torch.cat([val, torch.rand(6000, dtype=torch.float64)]), (T, N, N)).coalesce()
+band = tg.Band(tg.create_matrix_M(T, b))
+for dt in (torch.float32, torch.float64):
+    out = ops.mtransform_sparse(tg.SliceCSR.from_coo(C._indices(), C._values(), T, N, dtype=dt), band)
+    print(int(out.rowptr.sum()), int(out.col.to(torch.int64).sum()), out.nnz, repr(float(out.val.double().sum())))
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, TMGCN_MERGE_STAGED=flag)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 2
+
+
 def test_mtransform_sparse_zero_weight_and_cancellation(tg):
     """explicit zeros inside the band drop the source slice (nonzero(M[:, j]), ref: read_data.py:216);
     sums that cancel to 0.0 stay stored (coalesce never prunes)."""
