@@ -127,9 +127,11 @@ def test_mtransform_sparse_vs_oracle(tg, T, N, m, rho, b, norm):
     np.testing.assert_allclose(torch.cat([v_lo, v_hi]).cpu().double().numpy(), ref_val, rtol=2e-7, atol=0)
 
 
-def test_mtransform_sparse_staged_variant_is_bit_identical(tg):
-    """the shared-memory staged merge kernel (TMGCN_MERGE_STAGED=1) against the default kernel, in a subprocess
-    because the choice is latched on first use; includes hub rows that overflow the staging capacity."""
+def test_mtransform_sparse_fill_variants_agree(tg):
+    """the fill-pass variants of the sparse M-transform (thread per row; shared-memory staged with 1, 2 or 4
+    lanes per row; the automatic choice) in subprocesses, because the choice is latched on first use.  All of
+    them sum a row's contributions in the same order, so indices AND values are bit-identical.  Hub rows
+    overflow the staging capacity and take the kernel's global-memory path."""
     import os
     import subprocess
     import sys
@@ -146,13 +148,21 @@ C = torch.sparse_coo_tensor(torch.cat([idx, hub], 1), torch.cat([val, torch.rand
 band = tg.Band(tg.create_matrix_M(T, b))
 for dt in (torch.float32, torch.float64):
     out = ops.mtransform_sparse(tg.SliceCSR.from_coo(C._indices(), C._values(), T, N, dtype=dt), band)
-    print(int(out.rowptr.sum()), int(out.col.to(torch.int64).sum()), out.nnz, repr(float(out.val.double().sum())))
+    w = torch.arange(out.nnz, device=out.val.device, dtype=torch.float64) %% 97 + 1.0
+    print(int(out.rowptr.sum()), int((out.col.to(torch.int64) * w.long()).sum()), out.nnz,
+          repr(float((out.val.double() * w).sum())))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for flag in ("0", "1"):
-        env = dict(os.environ, TMGCN_MERGE_STAGED=flag)
-        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout)
-    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 2
+    outs = {}
+    for flag in ("0", "1", "2", "4", None):
+        env = dict(os.environ)
+        env.pop("TMGCN_MERGE_STAGED", None)
+        if flag is not None:
+            env["TMGCN_MERGE_STAGED"] = flag
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+        outs[flag] = [ln.split() for ln in r.stdout.strip().splitlines()]
+        assert len(outs[flag]) == 2
+    for flag in ("1", "2", "4", None):
+        assert outs[flag] == outs["0"], flag
 
 
 def test_mtransform_sparse_zero_weight_and_cancellation(tg):

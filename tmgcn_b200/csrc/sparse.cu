@@ -180,13 +180,250 @@ __global__ void __launch_bounds__(128) merge_rows(const int64_t *__restrict__ in
     if (COUNT_ONLY) out_counts[row] = count;
 }
 
-// Staged variant (opt-in, see launch_merge): a warp owns 32 consecutive rows of one output slice.  For every source
-// slice of the band those rows' entries are ONE contiguous range of the CSR, so the warp copies it into
-// shared memory with coalesced loads (every fetched sector is fully used; the thread-per-row kernel above
-// re-fetched a 32-byte sector for each 4-byte read: 195 GB of DRAM traffic for 16 GB of data) and the lanes
-// then run the same B-way register-cursor merge out of shared memory.  A block whose segment exceeds the
-// staging capacity (hub rows) falls back, warp-uniformly, to reading that source from global memory.
-template <int B, bool COUNT_ONLY, typename VT>
+// Staged variant (fill pass, see launch_merge).  A warp owns RW = 32/LPR consecutive rows of one output slice and
+// LPR lanes share a row, each holding CB = ceil(B/LPR) of its B cursors.  For every source slice of the band
+// the warp's rows are ONE contiguous range of the CSR, so the warp copies it into shared memory with coalesced
+// cp.async (every fetched sector is fully used; the thread-per-row kernel above re-fetches a 32-byte sector for
+// each 4-byte read: 195 GB of DRAM traffic for 16 GB of data) and the lanes then run the register-cursor merge
+// out of shared memory, branch-free: a step is min over own cursors -> min over the row's lanes (shuffles) ->
+// every cursor on the minimum contributes and reloads.  Splitting a row over LPR lanes divides both the staging
+// footprint per warp (more resident warps: the loop is latency-bound) and the serial work per step.
+// A block whose segments do not fit (hub rows) runs the same loop on global memory.
+// Sum order: ONE fp64 FMA chain over the row's cursors in ascending source-slice order, handed from lane to
+// lane of the row -- every variant produces the bits of the thread-per-row kernel.
+template <int CB, int LPR, bool COUNT_ONLY, typename VT>
+__device__ __forceinline__ int64_t merge_loop_global(const int32_t *__restrict__ colp, const VT *__restrict__ valp,
+                                               const int64_t (&gb)[CB], int32_t (&p)[CB], const int32_t (&e)[CB],
+                                               const double (&w)[CB], bool writer, int64_t obase,
+                                               int32_t *__restrict__ out_col, VT *__restrict__ out_val) {
+    int32_t cur[CB];
+    VT v[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) {
+        const bool in = p[k] < e[k];
+        cur[k] = in ? colp[gb[k] + p[k]] : INT_MAX;
+        v[k] = (!COUNT_ONLY && in) ? valp[gb[k] + p[k]] : (VT)0;
+    }
+    int64_t count = 0;
+    while (true) {
+        int m = cur[0];
+#pragma unroll
+        for (int k = 1; k < CB; ++k) m = min(m, cur[k]);
+#pragma unroll
+        for (int d = 1; d < LPR; d <<= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+        const bool row_done = m == INT_MAX;
+        if (LPR == 1) {
+            if (row_done) break;
+        } else {
+            if (__all_sync(0xffffffffu, row_done)) break;
+        }
+        const int mm = (LPR > 1 && row_done) ? -1 : m;                      // finished rows match nothing
+        double acc = 0.0;
+        if (!COUNT_ONLY) {
+            // ascending-slot chain across the row's lanes (see merge_loop_smem)
+#pragma unroll
+            for (int sI = 0; sI < LPR; ++sI) {
+                double part = acc;
+#pragma unroll
+                for (int k = 0; k < CB; ++k)
+                    if (cur[k] == mm) part = fma(w[k], (double)v[k], part);
+                acc = LPR == 1 ? part : __shfl_sync(0xffffffffu, part, (threadIdx.x & ~(LPR - 1)) + sI);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CB; ++k) p[k] += (cur[k] == mm) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+            const bool in = p[k] < e[k];
+            cur[k] = in ? colp[gb[k] + p[k]] : INT_MAX;
+            if (!COUNT_ONLY) v[k] = in ? valp[gb[k] + p[k]] : (VT)0;
+        }
+        if (!COUNT_ONLY) {
+            if (writer && !row_done) {
+                out_col[obase + count] = m;
+                out_val[obase + count] = (VT)acc;
+            }
+        }
+        count += row_done ? 0 : 1;
+    }
+    return count;
+}
+
+// Staged entries are interleaved {col, val}: 4 B (count pass), 8 B (fp32) or 16 B (fp64: col, pad, val), so a
+// cursor reload is ONE shared load at one address; cursors are absolute shared byte addresses.
+template <bool COUNT_ONLY, typename VT>
+struct StageEntry {
+    static constexpr int SIZE = COUNT_ONLY ? 4 : (sizeof(VT) == 4 ? 8 : 16);
+    static constexpr int VAL_OFF = sizeof(VT) == 4 ? 4 : 8;
+};
+
+// Register image of a staged value: fp32 values travel as raw bits so one v2.b32 load fills {col, val}.
+template <typename VT>
+struct ValReg {
+    using type = int32_t;
+};
+template <>
+struct ValReg<double> {
+    using type = double;
+};
+
+// One cursor, one step, as straight-line predicated PTX (the compiler's version of the same C spends ~14
+// instructions per cursor on selects and register moves; this is 7):
+//   hit = (col under the cursor == the step's minimum);  if hit: acc += w * val (fp64 FMA), cursor += 1 entry;
+//   reload {col, val} at the cursor, or INT_MAX when the row's list is exhausted.
+// With advance == false it is just the (re)load.
+template <bool COUNT_ONLY, typename VT, bool FMA = true>
+__device__ __forceinline__ void cursor_step(int32_t &c, typename ValReg<VT>::type &v, uint32_t &p, uint32_t e, int mm,
+                                            double w, double &acc) {
+    if (COUNT_ONLY) {
+        asm volatile(
+            "{\n .reg .pred h, q;\n"
+            " setp.eq.s32 h, %0, %3;\n"
+            " @h add.u32 %1, %1, 4;\n"
+            " setp.lt.u32 q, %1, %2;\n"
+            " mov.b32 %0, 0x7fffffff;\n"
+            " @q ld.shared.b32 %0, [%1];\n}"
+            : "+r"(c), "+r"(p)
+            : "r"(e), "r"(mm));
+    } else if (!FMA && sizeof(VT) == 4) {
+        asm volatile(
+            "{\n .reg .pred h, q;\n"
+            " setp.eq.s32 h, %0, %4;\n"
+            " @h add.u32 %2, %2, 8;\n"
+            " setp.lt.u32 q, %2, %3;\n"
+            " mov.b32 %0, 0x7fffffff;\n"
+            " @q ld.shared.v2.b32 {%0, %1}, [%2];\n}"
+            : "+r"(c), "+r"(*reinterpret_cast<int32_t *>(&v)), "+r"(p)
+            : "r"(e), "r"(mm));
+    } else if (!FMA) {
+        asm volatile(
+            "{\n .reg .pred h, q;\n"
+            " setp.eq.s32 h, %0, %4;\n"
+            " @h add.u32 %2, %2, 16;\n"
+            " setp.lt.u32 q, %2, %3;\n"
+            " mov.b32 %0, 0x7fffffff;\n"
+            " @q ld.shared.b32 %0, [%2];\n"
+            " @q ld.shared.b64 %1, [%2+8];\n}"
+            : "+r"(c), "+d"(*reinterpret_cast<double *>(&v)), "+r"(p)
+            : "r"(e), "r"(mm));
+    } else if (sizeof(VT) == 4) {
+        asm volatile(
+            "{\n .reg .pred h, q;\n .reg .f32 vf;\n .reg .f64 vd;\n"
+            " setp.eq.s32 h, %0, %5;\n"
+            " mov.b32 vf, %1;\n"
+            " selp.f32 vf, vf, 0f00000000, h;\n"          // w * (+0) leaves the fp64 chain unchanged
+            " cvt.f64.f32 vd, vf;\n"
+            " fma.rn.f64 %3, %6, vd, %3;\n"
+            " @h add.u32 %2, %2, 8;\n"
+            " setp.lt.u32 q, %2, %4;\n"
+            " mov.b32 %0, 0x7fffffff;\n"
+            " @q ld.shared.v2.b32 {%0, %1}, [%2];\n}"
+            : "+r"(c), "+r"(*reinterpret_cast<int32_t *>(&v)), "+r"(p), "+d"(acc)
+            : "r"(e), "r"(mm), "d"(w));
+    } else {
+        asm volatile(
+            "{\n .reg .pred h, q;\n .reg .f64 vd;\n"
+            " setp.eq.s32 h, %0, %5;\n"
+            " selp.f64 vd, %1, 0d0000000000000000, h;\n"
+            " fma.rn.f64 %3, %6, vd, %3;\n"
+            " @h add.u32 %2, %2, 16;\n"
+            " setp.lt.u32 q, %2, %4;\n"
+            " mov.b32 %0, 0x7fffffff;\n"
+            " @q ld.shared.b32 %0, [%2];\n"
+            " @q ld.shared.b64 %1, [%2+8];\n}"
+            : "+r"(c), "+d"(*reinterpret_cast<double *>(&v)), "+r"(p), "+d"(acc)
+            : "r"(e), "r"(mm), "d"(w));
+    }
+}
+
+// the accumulate half of cursor_step alone (split rows chain their lanes' partial sums one after another)
+template <typename VT>
+__device__ __forceinline__ void cursor_fma(int32_t c, typename ValReg<VT>::type v, int mm, double w, double &acc) {
+    if (sizeof(VT) == 4) {
+        asm volatile(
+            "{\n .reg .pred h;\n .reg .f32 vf;\n .reg .f64 vd;\n"
+            " setp.eq.s32 h, %1, %3;\n"
+            " mov.b32 vf, %2;\n"
+            " selp.f32 vf, vf, 0f00000000, h;\n"
+            " cvt.f64.f32 vd, vf;\n"
+            " fma.rn.f64 %0, %4, vd, %0;\n}"
+            : "+d"(acc)
+            : "r"(c), "r"(*reinterpret_cast<const int32_t *>(&v)), "r"(mm), "d"(w));
+    } else {
+        asm volatile(
+            "{\n .reg .pred h;\n .reg .f64 vd;\n"
+            " setp.eq.s32 h, %1, %3;\n"
+            " selp.f64 vd, %2, 0d0000000000000000, h;\n"
+            " fma.rn.f64 %0, %4, vd, %0;\n}"
+            : "+d"(acc)
+            : "r"(c), "d"(*reinterpret_cast<const double *>(&v)), "r"(mm), "d"(w));
+    }
+}
+
+template <int CB, int LPR, bool COUNT_ONLY, typename VT>
+__device__ __forceinline__ int64_t merge_loop_smem(uint32_t (&p)[CB], const uint32_t (&e)[CB], const double (&w)[CB],
+                                                   bool writer, int64_t obase, int32_t *__restrict__ out_col,
+                                                   VT *__restrict__ out_val) {
+    int32_t cur[CB];
+    typename ValReg<VT>::type v[CB];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < CB; ++k) {
+        v[k] = 0;
+        cur[k] = -2;                                                        // matches nothing: plain load
+        cursor_step<COUNT_ONLY, VT>(cur[k], v[k], p[k], e[k], -1, 0.0, acc);
+    }
+    int32_t *oc = out_col + obase;
+    VT *ov = out_val + obase;
+    int64_t count = 0;
+    while (true) {
+        int m = cur[0];
+#pragma unroll
+        for (int k = 1; k < CB; ++k) m = min(m, cur[k]);
+#pragma unroll
+        for (int d = 1; d < LPR; d <<= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+        const bool row_done = m == INT_MAX;
+        if (LPR == 1) {
+            if (row_done) break;
+        } else {
+            if (__all_sync(0xffffffffu, row_done)) break;
+        }
+        const int mm = (LPR > 1 && row_done) ? -1 : m;                      // finished rows match nothing
+        acc = 0.0;
+        if (LPR == 1) {
+#pragma unroll
+            for (int k = 0; k < CB; ++k) cursor_step<COUNT_ONLY, VT>(cur[k], v[k], p[k], e[k], mm, w[k], acc);
+        } else {
+            // one chain over the row's B cursors in ascending slot order, exactly the sum the single-lane
+            // variants form: lane `s` of the row continues from what lane s-1 handed over
+            if (!COUNT_ONLY) {
+#pragma unroll
+                for (int sI = 0; sI < LPR; ++sI) {
+                    double part = acc;
+#pragma unroll
+                    for (int k = 0; k < CB; ++k) cursor_fma<VT>(cur[k], v[k], mm, w[k], part);
+                    acc = __shfl_sync(0xffffffffu, part, (threadIdx.x & ~(LPR - 1)) + sI);
+                }
+            }
+            double unused = 0.0;
+#pragma unroll
+            for (int k = 0; k < CB; ++k)
+                cursor_step<COUNT_ONLY, VT, false>(cur[k], v[k], p[k], e[k], mm, 0.0, unused);
+        }
+        if (!COUNT_ONLY) {
+            if (writer && !row_done) {
+                *oc = m;
+                *ov = (VT)acc;
+            }
+            oc += row_done ? 0 : 1;
+            ov += row_done ? 0 : 1;
+        }
+        count += row_done ? 0 : 1;
+    }
+    return count;
+}
+
+template <int B, int LPR, bool COUNT_ONLY, typename VT>
 __global__ void __launch_bounds__(32) merge_rows_staged(const int64_t *__restrict__ in_rowptr,
                                                         const int32_t *__restrict__ in_col,
                                                         const VT *__restrict__ in_val, int T_out, int halo, int64_t N,
@@ -194,111 +431,105 @@ __global__ void __launch_bounds__(32) merge_rows_staged(const int64_t *__restric
                                                         int64_t *__restrict__ out_counts,
                                                         const int64_t *__restrict__ out_rowptr,
                                                         int32_t *__restrict__ out_col, VT *__restrict__ out_val) {
+    constexpr int RW = 32 / LPR;                 // rows per warp
+    constexpr int CB = (B + LPR - 1) / LPR;      // cursors per lane
     extern __shared__ __align__(16) uint8_t stage_raw[];
-    int32_t *scol = reinterpret_cast<int32_t *>(stage_raw);                 // [B][cap]
-    VT *sval = reinterpret_cast<VT *>(stage_raw + (size_t)B * cap * 4);     // [B][cap]   (fill pass only)
+    constexpr int ES = StageEntry<COUNT_ONLY, VT>::SIZE;
+    constexpr int VO = StageEntry<COUNT_ONLY, VT>::VAL_OFF;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_raw);   // [B][cap] entries of ES bytes
     const int lane = threadIdx.x;
-    const int64_t nblk = (N + 31) / 32;
+    const int sub = lane % LPR;                  // which share of the row's cursors this lane holds
+    const int rl = lane / LPR;                   // row of the block
+    const int64_t nblk = (N + RW - 1) / RW;
     const int64_t n_tasks = (int64_t)T_out * nblk;
     for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
         const int t = (int)(task / nblk);
-        const int64_t r0 = (task - (int64_t)t * nblk) * 32;
-        const int64_t i = r0 + lane;
+        const int64_t r0 = (task - (int64_t)t * nblk) * RW;
+        const int64_t i = r0 + rl;
         const bool live = i < N;
         const int64_t ic = live ? i : N - 1;                                // clamp for the pointer loads
-        int32_t pos[B], left[B], cur[B];
-        int64_t gbase[B];        // global position of staged element 0 (or of the lane's cursor when not staged)
-        bool staged[B];
-        double w[B];
-        // phase 1: row pointers of every source slice -- all loads are issued before any is consumed
-        int64_t p0s[B], p1s[B];
+        // phase 1: row pointers of this lane's cursors -- all loads are issued before any is consumed.
+        // Cursor slot kk = sub*CB + k walks source slice halo + t - (B-1-kk): ascending slot = ascending slice.
+        int64_t p0s[CB], p1s[CB];
+        double w[CB];
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
-            const int l = B - 1 - k;
+        for (int k = 0; k < CB; ++k) {
+            const int kk = sub * CB + k;
+            const int l = B - 1 - kk;
             p0s[k] = p1s[k] = 0;
             w[k] = 0.0;
-            staged[k] = false;                                              // "valid" until the bounds are known
-            if (l < b) {
+            if (l >= 0 && l < b) {
                 const int sl = halo + t - l;
                 const double wl = band_w[(int64_t)t * b + l];
                 if (sl >= 0 && wl != 0.0) {
-                    staged[k] = true;
                     w[k] = wl;
                     p0s[k] = in_rowptr[(int64_t)sl * N + ic];
                     p1s[k] = in_rowptr[(int64_t)sl * N + ic + 1];
                 }
             }
+            if (!live) p0s[k] = p1s[k];                                     // padding lanes own empty rows
         }
-        // phase 2: segment bounds via shuffles, then the staging copies as fire-and-forget cp.async (4 B each):
-        // all B segments are in flight together, one wait for the lot
+        // phase 2: segment bounds of every slot via shuffles (slot kk lives in sub-lane kk / CB), then the
+        // staging copies as fire-and-forget cp.async: all B segments are in flight together, one wait for the lot
+        bool fits = true;                                                   // warp-uniform
+        int64_t seg0s[CB];
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
-            int64_t p0 = p0s[k];
-            const int64_t p1 = p1s[k];
-            if (!live) p0 = p1;                                             // padding lanes own an empty row
-            const int64_t seg0 = __shfl_sync(0xffffffffu, p0, 0);
-            const int64_t seg1 = __shfl_sync(0xffffffffu, p1, 31);
-            const int64_t len = seg1 - seg0;
-            staged[k] = staged[k] && len <= cap;                            // warp-uniform
-            left[k] = (int32_t)(p1 - p0);
-            if (staged[k]) {
-                gbase[k] = seg0;
-                pos[k] = (int32_t)(p0 - seg0);
-                for (int64_t q = lane; q < len; q += 32) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
-                                     (uint32_t)__cvta_generic_to_shared(scol + k * cap + q)),
-                                 "l"(in_col + seg0 + q)
+        for (int kk = 0; kk < CB * LPR; ++kk) {
+            const int own = kk / CB, k = kk % CB;                           // compile-time after unrolling
+            const int64_t seg0 = __shfl_sync(0xffffffffu, p0s[k], own);
+            const int64_t seg1 = __shfl_sync(0xffffffffu, p1s[k], (RW - 1) * LPR + own);
+            if (own == sub) seg0s[k] = seg0;
+            fits = fits && (seg1 - seg0 <= cap);
+        }
+        if (fits) {
+#pragma unroll
+            for (int kk = 0; kk < CB * LPR; ++kk) {
+                const int own = kk / CB, k = kk % CB;
+                const int64_t seg0 = __shfl_sync(0xffffffffu, seg0s[k], own);
+                const int64_t seg1 = __shfl_sync(0xffffffffu, p1s[k], (RW - 1) * LPR + own);
+                const int64_t len = seg1 - seg0;
+                uint32_t dst = sbase + (uint32_t)(kk * cap + lane) * ES;
+                for (int64_t q = lane; q < len; q += 32, dst += 32 * ES) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(in_col + seg0 + q)
                                  : "memory");
                     if (!COUNT_ONLY) {
                         if (sizeof(VT) == 4)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
-                                             (uint32_t)__cvta_generic_to_shared(sval + k * cap + q)),
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + VO),
                                          "l"(in_val + seg0 + q)
                                          : "memory");
                         else
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
-                                             (uint32_t)__cvta_generic_to_shared(sval + k * cap + q)),
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + VO),
                                          "l"(in_val + seg0 + q)
                                          : "memory");
                     }
                 }
-            } else {
-                gbase[k] = p0;
-                pos[k] = 0;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        const bool writer = live && sub == 0;
+        const int64_t obase = (COUNT_ONLY || !writer) ? 0 : out_rowptr[(int64_t)t * N + i];
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
+        int64_t count;
+        if (fits) {
+            uint32_t p[CB], e[CB];
 #pragma unroll
-        for (int k = 0; k < B; ++k)
-            cur[k] = left[k] > 0 ? (staged[k] ? scol[k * cap + pos[k]] : in_col[gbase[k]]) : INT_MAX;
-        // phase 3: B-way merge, one row per lane
-        int64_t count = 0;
-        const int64_t obase = (COUNT_ONLY || !live) ? 0 : out_rowptr[(int64_t)t * N + i];
-        while (true) {
-            int m = cur[0];
-#pragma unroll
-            for (int k = 1; k < B; ++k) m = min(m, cur[k]);
-            if (m == INT_MAX) break;
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < B; ++k) {
-                if (cur[k] == m) {
-                    if (!COUNT_ONLY)
-                        acc += w[k] * (double)(staged[k] ? sval[k * cap + pos[k]] : in_val[gbase[k] + pos[k]]);
-                    ++pos[k];
-                    --left[k];
-                    cur[k] = left[k] > 0 ? (staged[k] ? scol[k * cap + pos[k]] : in_col[gbase[k] + pos[k]]) : INT_MAX;
-                }
+            for (int k = 0; k < CB; ++k) {
+                p[k] = sbase + (uint32_t)((sub * CB + k) * cap + (int32_t)(p0s[k] - seg0s[k])) * ES;
+                e[k] = p[k] + (uint32_t)(p1s[k] - p0s[k]) * ES;
             }
-            if (!COUNT_ONLY) {
-                out_col[obase + count] = m;
-                out_val[obase + count] = (VT)acc;
+            count = merge_loop_smem<CB, LPR, COUNT_ONLY, VT>(p, e, w, writer, obase, out_col, out_val);
+        } else {
+            int32_t p[CB], e[CB];
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                p[k] = 0;
+                e[k] = (int32_t)(p1s[k] - p0s[k]);
             }
-            ++count;
+            count = merge_loop_global<CB, LPR, COUNT_ONLY, VT>(in_col, in_val, p0s, p, e, w, writer, obase, out_col,
+                                                               out_val);
         }
-        if (COUNT_ONLY && live) out_counts[(int64_t)t * N + i] = count;
+        if (COUNT_ONLY && writer) out_counts[(int64_t)t * N + i] = count;
         __syncwarp();                                                       // staging buffers are reused by the next task
     }
 }
@@ -307,34 +538,72 @@ template <bool COUNT_ONLY, typename VT>
 static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const VT *in_val, int T_out, int halo,
                         int64_t N, const double *band_w, int b, int64_t *out_counts, const int64_t *out_rowptr,
                         int32_t *out_col, VT *out_val, cudaStream_t st) {
-    // The staged kernel cuts DRAM traffic 10x (ncu: 18 GB vs 205 GB for the 12-slice, 390 M-output case) but
-    // its 36 KB of staging per warp leaves 6 warps per SM and the ~300-instruction merge step then runs
-    // latency-bound (25 ms vs 20 ms for the thread-per-row kernel at full occupancy), so it is opt-in
-    // (TMGCN_MERGE_STAGED=1) until the merge step itself is cheaper.
-    static int use_staged = -1;
-    if (use_staged < 0) {
+    // Count pass: thread per row (cols only: issue-bound at full occupancy, faster than staging).
+    // Fill pass: the staged kernel when the rows are short enough for a warp's block to fit its staging
+    // buffers -- 1.9x faster on the 2 M-node shard (ncu: 18 GB of DRAM traffic instead of 205 GB for 390 M
+    // outputs) -- else thread per row.  TMGCN_MERGE_STAGED = 0 | 1 | 2 | 4 forces the fill variant (lanes per
+    // row; 0 = thread per row), TMGCN_MERGE_STAGE_KB the staging bytes per warp.
+    static int forced = -2;
+    static int stage_kb = 36;
+    if (forced == -2) {
         const char *e = getenv("TMGCN_MERGE_STAGED");
-        use_staged = (e && e[0] == '1') ? 1 : 0;
+        forced = e ? atoi(e) : -1;
+        const char *k = getenv("TMGCN_MERGE_STAGE_KB");
+        if (k && atoi(k) > 0) stage_kb = atoi(k);
     }
     const int threads = 128;
     const unsigned grid = (unsigned)ceil_div((int64_t)T_out * N, threads);
-    const size_t entry = 4 + (COUNT_ONLY ? 0 : sizeof(VT));
-    const int64_t n_tasks = (int64_t)T_out * ceil_div(N, 32);
+    constexpr size_t entry = StageEntry<COUNT_ONLY, VT>::SIZE;
+    int sel = 0;
+    int cap = 0;
+    if (!COUNT_ONLY && forced != 0) {
+        int bb = 2;                                                         // the template width b rounds up to
+        for (const int cand : {2, 4, 6, 8, 10, 12, 16, 20, 24, 32})
+            if (b <= cand) {
+                bb = cand;
+                break;
+            }
+        cap = (int)(((size_t)stage_kb * 1024) / ((size_t)bb * entry)) & ~15;
+        if (cap > 1024) cap = 1024;
+        if (cap < 16) cap = 16;
+        if (forced > 0) {
+            sel = forced;
+        } else {
+            // mean stored entries per source row decide how many rows a warp can stage (mean + 4 sigma of a
+            // Poisson block; longer blocks -- hub rows -- take the kernel's global-memory path)
+            int64_t nnz_in = 0;
+            const int64_t rows_in = (int64_t)(T_out + halo) * N;
+            TMGCN_CUDA(cudaMemcpyAsync(&nnz_in, in_rowptr + rows_in, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            TMGCN_CUDA(cudaStreamSynchronize(st));
+            const double mean = rows_in > 0 ? (double)nnz_in / (double)rows_in : 0.0;
+            for (const int ll : {1, 2}) {                                    // 4 lanes per row only pays when forced
+                const double need = mean * (32 / ll);
+                if (need + 4.0 * sqrt(need) + 16.0 <= (double)cap && ll <= bb) {
+                    sel = ll;
+                    break;
+                }
+            }
+        }
+    }
+#define TMGCN_MERGE_STAGED(BB, LL)                                                                               \
+    if constexpr (!COUNT_ONLY && BB >= LL) {                                                                     \
+        const size_t smem = (size_t)BB * cap * entry;                                                            \
+        const int64_t n_tasks = (int64_t)T_out * ceil_div(N, (int64_t)(32 / LL));                                \
+        auto kern = merge_rows_staged<BB, LL, COUNT_ONLY, VT>;                                                   \
+        TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        int per_sm = (int)((220 * 1024) / (smem + 1024));                                                        \
+        if (per_sm > 32) per_sm = 32;                                                                            \
+        int64_t g = (int64_t)sm_count() * per_sm;                                                                \
+        if (g > n_tasks) g = n_tasks;                                                                            \
+        kern<<<(unsigned)g, 32, smem, st>>>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b, cap,           \
+                                            out_counts, out_rowptr, out_col, out_val);                           \
+        return after_launch("merge_rows_staged<fill>");                                                          \
+    }
 #define TMGCN_MERGE(BB)                                                                                          \
     if (b <= BB) {                                                                                               \
-        if (use_staged) {                                                                                        \
-            /* ~36 KB of staging per warp: 6 resident warps per SM; capacity per source slice in entries */      \
-            int cap = (int)((36 * 1024) / (BB * entry)) & ~15;                                                   \
-            if (cap > 1024) cap = 1024;                                                                          \
-            const size_t smem = (size_t)BB * cap * entry;                                                        \
-            auto kern = merge_rows_staged<BB, COUNT_ONLY, VT>;                                                   \
-            TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-            int64_t g = (int64_t)sm_count() * (int64_t)((220 * 1024) / (smem + 1024));                            \
-            if (g > n_tasks) g = n_tasks;                                                                        \
-            kern<<<(unsigned)g, 32, smem, st>>>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b, cap,       \
-                                                out_counts, out_rowptr, out_col, out_val);                       \
-            return after_launch(COUNT_ONLY ? "merge_rows_staged<count>" : "merge_rows_staged<fill>");            \
-        }                                                                                                        \
+        if (sel == 1) TMGCN_MERGE_STAGED(BB, 1)                                                                  \
+        if (sel == 2) TMGCN_MERGE_STAGED(BB, 2)                                                                  \
+        if (sel == 4) TMGCN_MERGE_STAGED(BB, 4)                                                                  \
         merge_rows<BB, COUNT_ONLY, VT><<<grid, threads, 0, st>>>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, \
                                                                  b, out_counts, out_rowptr, out_col, out_val);   \
         return after_launch(COUNT_ONLY ? "merge_rows<count>" : "merge_rows<fill>");                              \
@@ -350,6 +619,7 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
     TMGCN_MERGE(24)
     TMGCN_MERGE(32)
 #undef TMGCN_MERGE
+#undef TMGCN_MERGE_STAGED
     set_error("mtransform_sparse: band width b=%d > 32 unsupported", b);
     return 1;
 }
