@@ -354,6 +354,233 @@ __global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? ((HAS_DY && HAS_D
     }
 }
 
+// ---- single-output halves of the factor apply (the low-rank backward's expand and reduce) ----------------
+// Pure streams: expand writes T*N*F floats from 2C per row, reduce reads T*N*F floats into a 2F x C sum.
+// One row per warp step, lane owns float4 columns lane + 32k; the row's 2C factors are ONE broadcast load
+// (all lanes, same address: a single 16/32 B request) instead of coalesced loads + 8 shuffles per row, the U
+// slice / the accumulators stay in registers, UNR rows are in flight per warp, rows interleave across the
+// grid's warps so neighbouring warps touch neighbouring rows.
+template <int CM>
+__device__ __forceinline__ void load_row_factors(const float *__restrict__ S, int64_t row, int C, bool vec,
+                                                 float (&s)[2][CM]) {
+    if (vec) {                                              // C == CM and 16-byte aligned rows
+        const float4 *q = reinterpret_cast<const float4 *>(S + row * (2 * CM));
+        float t[2 * CM];
+#pragma unroll
+        for (int i = 0; i < (2 * CM) / 4; ++i) {
+            const float4 v = __ldg(q + i);
+            t[4 * i] = v.x; t[4 * i + 1] = v.y; t[4 * i + 2] = v.z; t[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < CM; ++c) s[h][c] = t[h * CM + c];
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < CM; ++c) s[h][c] = c < C ? __ldg(S + row * (2 * C) + h * C + c) : 0.f;
+    }
+}
+
+template <int CM, int NCH, int UNR>
+__global__ void __launch_bounds__(256) factor_expand_kernel(const float *__restrict__ u, const float *__restrict__ S,
+                                                            int64_t n_rows, float *__restrict__ dy, int F, int C,
+                                                            int vec) {
+    const int lane = threadIdx.x & 31;
+    float ur[2][NCH][4][CM];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int c = 0; c < CM; ++c) {
+                    const int f = 4 * (lane + 32 * k) + v;
+                    ur[h][k][v][c] = (f < F && c < C) ? __ldg(u + ((int64_t)h * F + f) * C + c) : 0.f;
+                }
+    const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int64_t base = w0; base < n_rows; base += W * UNR) {
+        float s[UNR][2][CM];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int64_t row = base + j * W;
+            if (row < n_rows) load_row_factors<CM>(S, row, C, vec != 0, s[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int64_t row = base + j * W;
+            if (row >= n_rows) break;
+            bool touched = false;                           // untouched rows get exact zeros whatever U holds
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int c = 0; c < CM; ++c) touched = touched || (s[j][h][c] != 0.f);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int f0 = 4 * (lane + 32 * k);
+                if (f0 < F) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (touched) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+#pragma unroll
+                            for (int c = 0; c < CM; ++c) {
+                                o[v] = fmaf(s[j][0][c], ur[0][k][v][c], o[v]);
+                                o[v] = fmaf(s[j][1][c], ur[1][k][v][c], o[v]);
+                            }
+                    }
+                    st_stream_f4(reinterpret_cast<float4 *>(dy + row * F + f0), make_float4(o[0], o[1], o[2], o[3]));
+                }
+            }
+        }
+    }
+}
+
+// expand, C == CM and aligned S: a warp takes 32 consecutive rows, lane j fetches row j's 2C factors (one
+// coalesced request for the block) and the rows are then written one after another with the factors broadcast
+// by shuffles -- 32 rows of stores ride on a single load latency, which is what a pure write stream needs
+// (the per-row-load variant above reaches 4.5 TB/s, write-only peak is 7.5).
+template <int CM, int NCH>
+__global__ void __launch_bounds__(256) factor_expand32_kernel(const float *__restrict__ u, const float *__restrict__ S,
+                                                              int64_t n_rows, float *__restrict__ dy, int F) {
+    const int lane = threadIdx.x & 31;
+    float ur[2][NCH][4][CM];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int c = 0; c < CM; ++c) {
+                    const int f = 4 * (lane + 32 * k) + v;
+                    ur[h][k][v][c] = f < F ? __ldg(u + ((int64_t)h * F + f) * CM + c) : 0.f;
+                }
+    const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_blk = (n_rows + 31) / 32;
+    for (int64_t blk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n_blk; blk += W) {
+        const int64_t row0 = blk * 32;
+        float mine[2 * CM];
+#pragma unroll
+        for (int i = 0; i < 2 * CM; ++i) mine[i] = 0.f;
+        if (row0 + lane < n_rows) {
+            const float4 *q = reinterpret_cast<const float4 *>(S + (row0 + lane) * (2 * CM));
+#pragma unroll
+            for (int i = 0; i < (2 * CM) / 4; ++i) {
+                const float4 t4 = __ldg(q + i);
+                mine[4 * i] = t4.x; mine[4 * i + 1] = t4.y; mine[4 * i + 2] = t4.z; mine[4 * i + 3] = t4.w;
+            }
+        }
+        const int n_here = (int)min((int64_t)32, n_rows - row0);
+#pragma unroll 4
+        for (int j = 0; j < n_here; ++j) {
+            float sj[2 * CM];
+            bool touched = false;                           // untouched rows get exact zeros whatever U holds
+#pragma unroll
+            for (int i = 0; i < 2 * CM; ++i) {
+                sj[i] = __shfl_sync(0xffffffffu, mine[i], j);
+                touched = touched || (sj[i] != 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int f0 = 4 * (lane + 32 * k);
+                if (f0 < F) {
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (touched) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+#pragma unroll
+                            for (int c = 0; c < CM; ++c) {
+                                o[v] = fmaf(sj[c], ur[0][k][v][c], o[v]);
+                                o[v] = fmaf(sj[CM + c], ur[1][k][v][c], o[v]);
+                            }
+                    }
+                    st_stream_f4(reinterpret_cast<float4 *>(dy + (row0 + j) * F + f0),
+                                 make_float4(o[0], o[1], o[2], o[3]));
+                }
+            }
+        }
+    }
+}
+
+template <int CM, int NCH, int UNR>
+__global__ void __launch_bounds__(256) factor_reduce_kernel(const float *__restrict__ y, const float *__restrict__ S,
+                                                            int64_t n_rows, float *__restrict__ du_partial, int F,
+                                                            int C, int vec) {
+    extern __shared__ float red[];                          // [8 warps][2F*C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[2][NCH][4][CM];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int c = 0; c < CM; ++c) acc[h][k][v][c] = 0.f;
+    const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int64_t base = w0; base < n_rows; base += W * UNR) {
+        float s[UNR][2][CM];
+        float4 yv[UNR][NCH];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int64_t row = base + j * W;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int f0 = 4 * (lane + 32 * k);
+                yv[j][k] = (row < n_rows && f0 < F) ? ld_stream_f4(reinterpret_cast<const float4 *>(y + row * F + f0))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (row < n_rows) {
+                load_row_factors<CM>(S, row, C, vec != 0, s[j]);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int c = 0; c < CM; ++c) s[j][h][c] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j)
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const float yy[4] = {yv[j][k].x, yv[j][k].y, yv[j][k].z, yv[j][k].w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+#pragma unroll
+                    for (int c = 0; c < CM; ++c) {
+                        acc[0][k][v][c] = fmaf(yy[v], s[j][0][c], acc[0][k][v][c]);
+                        acc[1][k][v][c] = fmaf(yy[v], s[j][1][c], acc[1][k][v][c]);
+                    }
+            }
+    }
+    // block reduction in fixed warp order, then one partial per block
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int f = 4 * (lane + 32 * k) + v;
+                if (f < F) {
+#pragma unroll
+                    for (int c = 0; c < CM; ++c)
+                        if (c < C) red[warp * 2 * F * C + (h * F + f) * C + c] = acc[h][k][v][c];
+                }
+            }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 2 * F * C; i += blockDim.x) {
+        float sum = 0.f;
+        for (int w = 0; w < nw; ++w) sum += red[w * 2 * F * C + i];
+        du_partial[(int64_t)blockIdx.x * 2 * F * C + i] = sum;
+    }
+}
+
 __global__ void reduce_partials_edge(const float *__restrict__ partial, float *__restrict__ out, int n_chunks,
                                      int n_elem) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,6 +704,53 @@ int tmgcn_edge_factor_apply(const float *y, const float *u, const float *S, floa
     const int per_lane = v4 ? 4 : 1;
     const int nch = (F + 32 * per_lane - 1) / (32 * per_lane);
     TMGCN_REQUIRE(nch <= 4, "edge_factor_apply: F=%d too large", F);
+    const int cm = C <= 2 ? 2 : (C <= 4 ? 4 : 8);
+    if (v4 && (dy == nullptr) != (du == nullptr) && nch * cm <= 4) {
+        // one output only: the streaming kernels
+        const int vec = (C == cm && (uintptr_t)S % 16 == 0) ? 1 : 0;
+        int grid = 0;
+#define TMGCN_STREAM(CMX, K)                                                                                      \
+    if (cm == CMX && nch == K) {                                                                                  \
+        if (dy && vec) {                                                                                          \
+            auto kern = factor_expand32_kernel<CMX, K>;                                                           \
+            int per_sm = 1;                                                                                       \
+            TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));                     \
+            grid = sm_count() * (per_sm < 1 ? 1 : per_sm);                                                        \
+            const int64_t want = ceil_div(n_rows, 8 * 32);                                                        \
+            if (grid > want) grid = (int)want;                                                                    \
+            kern<<<grid, 256, 0, st>>>(u, S, n_rows, dy, F);                                                      \
+        } else if (dy) {                                                                                          \
+            auto kern = factor_expand_kernel<CMX, K, 4>;                                                          \
+            int per_sm = 1;                                                                                       \
+            TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));                     \
+            grid = sm_count() * (per_sm < 1 ? 1 : per_sm);                                                        \
+            const int64_t want = ceil_div(n_rows, 8);                                                             \
+            if (grid > want) grid = (int)want;                                                                    \
+            kern<<<grid, 256, 0, st>>>(u, S, n_rows, dy, F, C, vec);                                              \
+        } else {                                                                                                  \
+            auto kern = factor_reduce_kernel<CMX, K, 4>;                                                          \
+            const size_t rsm = (size_t)8 * n_u * sizeof(float);                                                   \
+            if (rsm > 48 * 1024)                                                                                  \
+                TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));    \
+            int per_sm = 1;                                                                                       \
+            TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, rsm));                   \
+            if (per_sm < 1) per_sm = 1;                                                                           \
+            if (per_sm > 4) per_sm = 4; /* the partial workspace holds 4 CTAs per SM */                           \
+            grid = sm_count() * per_sm;                                                                           \
+            const int64_t want = ceil_div(n_rows, 8);                                                             \
+            if (grid > want) grid = (int)want;                                                                    \
+            kern<<<grid, 256, rsm, st>>>(y, S, n_rows, partial, F, C, vec);                                       \
+        }                                                                                                         \
+    }
+        TMGCN_STREAM(2, 1) TMGCN_STREAM(2, 2) TMGCN_STREAM(4, 1)
+#undef TMGCN_STREAM
+        if (after_launch(dy ? "factor_expand" : "factor_reduce")) return 1;
+        if (du) {
+            reduce_partials_edge<<<(unsigned)ceil_div(n_u, 256), 256, 0, st>>>(partial, du, grid, n_u);
+            if (after_launch("reduce_partials_edge")) return 1;
+        }
+        return 0;
+    }
     const size_t smem = (size_t)n_u * sizeof(float) * (du ? 9 : 1);
     TMGCN_REQUIRE(smem <= 200 * 1024, "edge_factor_apply: 2*F*C too large");
     int grid = 0;
