@@ -27,6 +27,13 @@ __all__ = [
     "layer_forward",
     "layer_fwd_bwd",
     "normalise_adjacency",
+    "compute_f1",
+    "create_node_features",
+    "split_data",
+    "average_precision_class0",
+    "row_mrr",
+    "compute_MAP_MRR",
+    "load_data_mat",
     "make_symmetric",
     "edge_life",
     "laplacian_transformation",
@@ -409,3 +416,129 @@ def create_sparse(idx, val, start, end):
     out = idx[:, sel].copy()
     out[0] -= start
     return out, val[sel]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# data formats and metrics around the path -- numpy, small inputs only
+# ---------------------------------------------------------------------------------------------------------
+def compute_f1(guess, target):
+    """ref: ehf:530-538 -- class 0 is the positive class."""
+    guess, target = np.asarray(guess), np.asarray(target)
+    tp = float(np.sum((guess == 0) & (target == 0)))
+    fp = float(np.sum((guess == 0) & (target != 0)))
+    fn = float(np.sum((guess != 0) & (target == 0)))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        precision = np.float64(tp) / np.float64(tp + fp)
+        recall = np.float64(tp) / np.float64(tp + fn)
+        f1 = 2 * (precision * recall) / (precision + recall)
+    return precision, recall, f1
+
+
+def create_node_features(A_idx, A_val, T, N, S_train, S_val, S_test, same_block_size):
+    """ref: ehf:597-610 -- column sums and row sums of every slice in an fp32 buffer, blocks returned as fp64."""
+    X = np.zeros((T, N, 2), dtype=np.float32)
+    for (t, i, j), v in zip(np.asarray(A_idx).T, np.asarray(A_val)):
+        X[t, j, 0] += np.float32(v)
+        X[t, i, 1] += np.float32(v)
+    X = X.astype(np.float64)
+    if same_block_size:
+        return X[0:S_train], X[S_val:S_train + S_val], X[S_val + S_test:]
+    return X[0:S_train], X[S_train:S_train + S_val], X[S_train + S_val:]
+
+
+def split_data(edges_aug, labels, S_train, S_val, S_test, same_block_size):
+    """ref: ehf:612-655 (returns numpy arrays in the reference's order)."""
+    edges_aug, labels = np.asarray(edges_aug), np.asarray(labels)
+
+    def cut(lo, hi):
+        m = edges_aug[0] >= lo
+        if hi is not None:
+            m &= edges_aug[0] < hi
+        e = edges_aug[:, m].copy()
+        e[0] -= lo
+        later = e[:, e[0] != 0].copy()
+        later[0] -= 1
+        return e, labels[m], later
+    tr = cut(0, S_train)
+    if same_block_size:
+        va, te = cut(S_val, S_train + S_val), cut(S_val + S_test, None)
+        K_val = int(np.sum(va[0][0] - (S_train - S_val - 1) > 0))
+        K_test = int(np.sum(te[0][0] - (S_train - S_test - 1) > 0))
+        return (*tr, *va, K_val, *te, K_test)
+    va, te = cut(S_train, S_train + S_val), cut(S_train + S_val, None)
+    return (*tr, *va, *te)
+
+
+def average_precision_class0(true_classes, scores):
+    """What ehf:711 asks of sklearn: AP = sum_n (R_n - R_{n-1}) P_n over the distinct score thresholds in
+    descending order, with class 0 as the positive label."""
+    y = (np.asarray(true_classes) == 0)
+    s = np.asarray(scores)
+    order = np.argsort(-s, kind="mergesort")
+    y, s = y[order], s[order]
+    n_pos = float(y.sum())
+    ap, tp, prev_recall = 0.0, 0.0, 0.0
+    k = 0
+    while k < len(s):
+        e = k
+        while e < len(s) and s[e] == s[k]:
+            tp += float(y[e])
+            e += 1
+        recall = tp / n_pos
+        ap += (recall - prev_recall) * (tp / e)
+        prev_recall = recall
+        k = e
+    return ap
+
+
+def row_mrr(pred_row, true_row):
+    """ref: ehf:669-681 -- mean reciprocal rank of the label-0 cells of one dense row."""
+    existing = np.asarray(true_row) == 0
+    order = np.flip(np.argsort(pred_row))
+    ranks = np.arange(1, len(pred_row) + 1, dtype=np.float64)[existing[order]]
+    return (1.0 / ranks).sum() / ranks.shape[0]
+
+
+def compute_MAP_MRR(output, target, edges):
+    """ref: ehf:684-729 -- per-slice MAP (softmax score of class 0) and MRR (raw column 0 scattered into a dense
+    matrix, duplicates added, rows holding a label-1 cell), weighted by the slices' edge counts."""
+    output, target, edges = np.asarray(output), np.asarray(target), np.asarray(edges)
+    probs = torch.softmax(torch.from_numpy(np.ascontiguousarray(output)), dim=1)[:, 0].numpy()     # ehf:706
+    MAP = MRR = 0.0
+    for k in np.unique(edges[0]):
+        m = edges[0] == k
+        w = m.sum() / float(len(m))
+        adj = edges[1:3, m]
+        pred = np.zeros((adj[0].max() + 1, adj[1].max() + 1), dtype=output.dtype)
+        true = np.zeros(pred.shape, dtype=np.int64)
+        np.add.at(pred, (adj[0], adj[1]), output[m, 0])
+        np.add.at(true, (adj[0], adj[1]), target[m])
+        rows = [row_mrr(pred[i], true[i]) for i in range(pred.shape[0]) if (true[i] == 1).any()]
+        MRR += (np.mean(rows) if rows else np.nan) * w
+        MAP += average_precision_class0(target[m], probs[m]) * w
+    return MAP, MRR
+
+
+def load_data_mat(path, S_train, S_val, S_test, transformed):
+    """ref: ehf:542-595 -- the .mat wire format (1-based nnz x 3 subs, nnz x 1 vals) as plain (idx, val) pairs:
+    returns (A_labels, blocks, N[, M]) with blocks = three lists of per-slice (idx2, val) pairs."""
+    import scipy.io as sio
+    saved = sio.loadmat(path)
+
+    def coo(name, shape=None):
+        subs = np.asarray(saved[name + "_subs"]).astype(np.int64) - 1
+        vals = np.asarray(saved[name + "_vals"], dtype=np.float64).reshape(-1)
+        order = np.lexsort((subs[:, 2], subs[:, 1], subs[:, 0]))
+        return subs[order].T, vals[order]
+    a_idx, a_val = coo("A_labels")
+    T, N = int(a_idx[0].max()) + 1, int(max(a_idx[1].max(), a_idx[2].max())) + 1
+
+    def slices(idx, val, lo, hi):
+        return [(idx[1:3, idx[0] == j], val[idx[0] == j]) for j in range(lo, hi)]
+    if transformed:
+        blocks = [slices(*coo(n), 0, S_train) for n in ("Ct_train", "Ct_val", "Ct_test")]
+        return (a_idx, a_val), blocks, N, np.asarray(saved["M"], dtype=np.float64)
+    c_idx, c_val = coo("C")
+    blocks = [slices(c_idx, c_val, 0, S_train), slices(c_idx, c_val, S_train, S_train + S_val),
+              slices(c_idx, c_val, S_train + S_val, S_train + S_val + S_test)]
+    return (a_idx, a_val), blocks, N

@@ -29,4 +29,9 @@ def golden_models():
     return np.load(os.path.join(GOLDEN, "models.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_data():
+    return np.load(os.path.join(GOLDEN, "data_helpers.npz"))
+
+
 MPRODUCT_CASES = ["t8n50b3", "t8n50b3norm", "t12n33b20", "t5n17b1", "t9n40raw"]

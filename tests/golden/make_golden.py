@@ -288,7 +288,95 @@ def gen_preprocess():
     print("preprocess.npz", {k: v.shape for k, v in d.items() if k.endswith("_idx")})
 
 
+def gen_data_helpers():
+    """ehf:530-538 (compute_f1), 542-595 (load_data), 597-610 (create_node_features), 612-655 (split_data),
+    669-729 (MRR / MAP) of the unmodified reference on a small random dataset in the MATLAB wire format of
+    read_data.m:210-232 (``*_subs`` = nnz x 3, 1-based; ``*_vals`` = nnz x 1).
+
+    Two environment shims, neither touches the reference's arithmetic: ``np.float`` (removed from numpy 1.24,
+    used at ehf:677) is aliased to ``float``, and the subs are stored with an integer dtype because
+    ``torch.Size`` no longer accepts the numpy floats MATLAB writes (ehf:549-550)."""
+    import scipy.io as sio
+    np.float = float
+    ns = load_ref_functions(3)
+    T, N, S_train, S_val, S_test = 10, 15, 6, 2, 2
+    g = t.Generator().manual_seed(77)
+    n = 170
+    idx = t.stack([t.randint(0, T, (n,), generator=g), t.randint(0, N, (n,), generator=g),
+                   t.randint(0, N, (n,), generator=g)])
+    idx[:, 0] = t.tensor([T - 1, N - 1, N - 1])                      # pins the sizes load_data infers
+    lab = t.randint(0, 2, (n,), generator=g).double() * 2 - 1          # chess-style +-1 labels
+    A_labels = t.sparse_coo_tensor(idx, lab, (T, N, N)).coalesce()
+    C = random_coo(T, N, 0.12, 78)
+    M = ref_M_normalised(S_train, 3)
+
+    def window(lo):
+        sel = (C._indices()[0] >= lo) & (C._indices()[0] < lo + S_train)
+        i = C._indices()[:, sel].clone()
+        i[0] -= lo
+        return t.sparse_coo_tensor(i, C._values()[sel], (S_train, N, N)).coalesce()
+    Ct = {"train": ns["func_MProduct"](window(0), M), "val": ns["func_MProduct"](window(S_val), M),
+          "test": ns["func_MProduct"](window(S_val + S_test), M)}
+
+    def mat(sp):
+        return sp._indices().t().numpy().astype(np.int64) + 1, sp._values().numpy().astype(np.float64)[:, None]
+    m = {"M": M.numpy()}
+    for name, sp in [("A_labels", A_labels), ("C", C)] + [("Ct_" + k, v) for k, v in Ct.items()]:
+        m[name + "_subs"], m[name + "_vals"] = mat(sp)
+    sio.savemat(os.path.join(OUT, "data_helpers.mat"), m, do_compression=True)
+
+    d = {"sizes": np.array([T, N, S_train, S_val, S_test])}
+
+    def put(name, sp):
+        sp = sp.coalesce()
+        d[name + "_idx"], d[name + "_val"], d[name + "_shape"] = sp._indices().numpy(), sp._values().numpy(), np.array(sp.shape)
+    out = ehf.load_data(OUT + "/", "data_helpers.mat", S_train, S_val, S_test, True)
+    put("tr_A", out[0]); put("tr_A_labels", out[1])
+    for k, lst in zip(("train", "val", "test"), out[2:5]):
+        for j, sl in enumerate(lst):
+            put("tr_Ct_%s_%d" % (k, j), sl)
+    d["tr_N"], d["tr_M"] = np.array(int(out[5])), out[6].numpy()
+    out2 = ehf.load_data(OUT + "/", "data_helpers.mat", S_train, S_val, S_test, False)
+    for k, lst in zip(("train", "val", "test"), out2[2:5]):
+        d["raw_C_%s_len" % k] = np.array(len(lst))
+        for j, sl in enumerate(lst):
+            put("raw_C_%s_%d" % (k, j), sl)
+    A = out[0]
+    for sb in (True, False):
+        for k, x in zip(("train", "val", "test"), ehf.create_node_features(A, S_train, S_val, S_test, sb)):
+            d["X_%s_sb%d" % (k, sb)] = x.numpy()
+    # edges = stored entries + random "negative" pairs, labels 0 (existing) / 1 (added), sorted by time as
+    # augment_edges leaves them (ehf:518-525)
+    edges = A_labels._indices()
+    neg = t.stack([t.randint(0, T, (90,), generator=g), t.randint(0, N, (90,), generator=g),
+                   t.randint(0, N, (90,), generator=g)])
+    e_all = t.cat([edges, neg], 1)
+    l_all = t.cat([t.zeros(edges.shape[1], dtype=t.long), t.ones(90, dtype=t.long)])
+    _, order = e_all[0].sort()
+    e_all, l_all = e_all[:, order], l_all[order]
+    d["edges_aug"], d["labels"] = e_all.numpy(), l_all.numpy()
+    names_sb = ["edges_train", "target_train", "e_train", "edges_val", "target_val", "e_val", "K_val", "edges_test",
+                "target_test", "e_test", "K_test"]
+    names = [x for x in names_sb if not x.startswith("K_")]
+    for sb, nm in ((True, names_sb), (False, names)):
+        res = ehf.split_data(e_all.clone(), l_all.clone(), S_train, S_val, S_test, sb)
+        for k, x in zip(nm, res):
+            d["split_sb%d_%s" % (sb, k)] = np.asarray(x)
+    guess = t.randint(0, 2, (300,), generator=g)
+    target = t.randint(0, 2, (300,), generator=g)
+    d["f1_guess"], d["f1_target"] = guess.numpy(), target.numpy()
+    d["f1_out"] = np.array([float(x) for x in ehf.compute_f1(guess, target)])
+    for dt, tag in ((t.float32, "f32"), (t.float64, "f64")):
+        logits = t.randn(e_all.shape[1], 2, generator=g, dtype=t.float64).to(dt)
+        MAP, MRR = ehf.compute_MAP_MRR(logits, l_all, e_all)
+        d["metric_logits_" + tag] = logits.numpy()
+        d["metric_out_" + tag] = np.array([float(MAP), float(MRR)])
+    np.savez_compressed(os.path.join(OUT, "data_helpers.npz"), **d)
+    print("data_helpers.npz", len(d), "MAP/MRR", d["metric_out_f32"], d["metric_out_f64"], "f1", d["f1_out"])
+
+
 if __name__ == "__main__":
+    gen_data_helpers()
     gen_preprocess()
     gen_mproduct()
     gen_chess()

@@ -101,8 +101,10 @@ class _Base(nn.Module):
 
     @staticmethod
     def _fresh(At, X, edges) -> bool:
-        # the reference's dispatch rule, verbatim semantics (ref: ehf:212, 316, 476)
-        return type(At) == list and type(X) == torch.Tensor and type(edges) == torch.Tensor
+        # the reference's dispatch rule (ref: ehf:212, 316, 476): a Python list of slices means "new inputs";
+        # a ready SliceCSR (what data.load_data returns) counts as one too
+        return ((type(At) == list or isinstance(At, SliceCSR)) and type(X) == torch.Tensor
+                and type(edges) == torch.Tensor)
 
     @staticmethod
     def _param(*shape) -> nn.Parameter:
