@@ -140,17 +140,18 @@ import sys, torch
 sys.path.insert(0, %r)
 import tmgcn_b200 as tg
 from tmgcn_b200 import ops, synth
-T, N, b = 14, 3000, 10
+T, N = 14, 3000
 torch.manual_seed(11)
 idx, val = synth.synth_coo(N, T, 20000, 0.8, seed=3)
 hub = torch.stack([torch.randint(0, T, (6000,)), torch.full((6000,), 7), torch.randint(0, N, (6000,))])
 C = torch.sparse_coo_tensor(torch.cat([idx, hub], 1), torch.cat([val, torch.rand(6000, dtype=torch.float64)]), (T, N, N)).coalesce()
-band = tg.Band(tg.create_matrix_M(T, b))
-for dt in (torch.float32, torch.float64):
-    out = ops.mtransform_sparse(tg.SliceCSR.from_coo(C._indices(), C._values(), T, N, dtype=dt), band)
-    w = torch.arange(out.nnz, device=out.val.device, dtype=torch.float64) %% 97 + 1.0
-    print(int(out.rowptr.sum()), int((out.col.to(torch.int64) * w.long()).sum()), out.nnz,
-          repr(float((out.val.double() * w).sum())))
+for b in (2, 5, 10, 24):
+    band = tg.Band(tg.create_matrix_M(T, b))
+    for dt in (torch.float32, torch.float64):
+        out = ops.mtransform_sparse(tg.SliceCSR.from_coo(C._indices(), C._values(), T, N, dtype=dt), band)
+        w = torch.arange(out.nnz, device=out.val.device, dtype=torch.float64) %% 97 + 1.0
+        print(b, int(out.rowptr.sum()), int((out.col.to(torch.int64) * w.long()).sum()), out.nnz,
+              repr(float((out.val.double() * w).sum())))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     for flag in ("0", "1", "2", "4", None):
@@ -160,7 +161,7 @@ for dt in (torch.float32, torch.float64):
             env["TMGCN_MERGE_STAGED"] = flag
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
         outs[flag] = [ln.split() for ln in r.stdout.strip().splitlines()]
-        assert len(outs[flag]) == 2
+        assert len(outs[flag]) == 8
     for flag in ("1", "2", "4", None):
         assert outs[flag] == outs["0"], flag
 

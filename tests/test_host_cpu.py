@@ -3,6 +3,7 @@ declares, and the host logic (band extraction, M construction, input generator).
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -114,3 +115,38 @@ def test_synth_generator_matches_reference_preparation():
     # temporal persistence: consecutive slices share most of their pattern at rho = 0.8
     shared = (struct[1:] & struct[:-1]).sum().item() / struct[1:].sum().item()
     assert shared > 0.55
+
+
+# ---------------------------------------------------------------- bench.py contract
+_BENCH_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+               "vs_baseline", "dtype", "data", "config"}
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm: needs no GPU) prints exactly one JSON line on stdout with the
+    contract's keys, its own cpu_baseline and an e2e block without copies."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-nodes", "1500", "--cpu-slices", "4"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and _BENCH_KEYS <= set(d)
+    assert d["unit"] == "slice-edges/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_committed_bench_profile_has_the_contract_keys():
+    import json
+    with open(os.path.join(ROOT, "profiles", "r01_bench_final.json")) as f:
+        d = json.loads(f.read().strip().splitlines()[-1])
+    assert _BENCH_KEYS | {"clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"} <= set(d)
+    assert d["gpu_launches"] > 0 and d["roofline"]["bound"] in ("hbm", "tensor")
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["vs_baseline"] is None                      # BASELINE.md holds no published number for this metric
