@@ -461,19 +461,29 @@ __global__ void __launch_bounds__(256) factor_expand32_kernel(const float *__res
                 }
     const int64_t W = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_blk = (n_rows + 31) / 32;
-    for (int64_t blk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < n_blk; blk += W) {
-        const int64_t row0 = blk * 32;
-        float mine[2 * CM];
+    // the factors of the warp's NEXT block are requested before this block's 32 rows of stores go out
+    auto fetch = [&](int64_t blk, float (&dst)[2 * CM]) {
 #pragma unroll
-        for (int i = 0; i < 2 * CM; ++i) mine[i] = 0.f;
-        if (row0 + lane < n_rows) {
-            const float4 *q = reinterpret_cast<const float4 *>(S + (row0 + lane) * (2 * CM));
+        for (int i = 0; i < 2 * CM; ++i) dst[i] = 0.f;
+        const int64_t row = blk * 32 + lane;
+        if (blk < n_blk && row < n_rows) {
+            const float4 *q = reinterpret_cast<const float4 *>(S + row * (2 * CM));
 #pragma unroll
             for (int i = 0; i < (2 * CM) / 4; ++i) {
                 const float4 t4 = __ldg(q + i);
-                mine[4 * i] = t4.x; mine[4 * i + 1] = t4.y; mine[4 * i + 2] = t4.z; mine[4 * i + 3] = t4.w;
+                dst[4 * i] = t4.x; dst[4 * i + 1] = t4.y; dst[4 * i + 2] = t4.z; dst[4 * i + 3] = t4.w;
             }
         }
+    };
+    const int64_t blk0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float next[2 * CM];
+    fetch(blk0, next);
+    for (int64_t blk = blk0; blk < n_blk; blk += W) {
+        const int64_t row0 = blk * 32;
+        float mine[2 * CM];
+#pragma unroll
+        for (int i = 0; i < 2 * CM; ++i) mine[i] = next[i];
+        fetch(blk + W, next);
         const int n_here = (int)min((int64_t)32, n_rows - row0);
 #pragma unroll 4
         for (int j = 0; j < n_here; ++j) {
