@@ -181,7 +181,8 @@ size_t tmgcn_edge_readout_bwd_ws_bytes(int64_t n_rows, int F, int C);
  * class_sums  : S[row, h, c] = sum over incident (e, h) of dout[e, c]            S is (n_rows, 2, C)
  * factor_apply: dy[row, f] = sum_{h,c} S[row,h,c] * u[hF+f, c]     (if dy)      "expand"
  *               du[hF+f, c] = sum_rows y[row, f] * S[row,h,c]      (if du)      "reduce"
- * ws: tmgcn_edge_factor_ws_bytes(F, C) bytes, needed only when du is requested. */
+ * ws: tmgcn_edge_factor_ws_bytes(F, C) bytes, needed only when du is requested.
+ * dout / perm may be null when there is no edge at all (inc_ptr all zero). */
 size_t tmgcn_edge_factor_ws_bytes(int F, int C);
 int tmgcn_edge_class_sums(const float *dout, const int64_t *inc_ptr, const int64_t *perm, float *S, int64_t n_rows,
                           int C, void *stream);

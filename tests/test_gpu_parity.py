@@ -702,3 +702,61 @@ def test_graph_preparation_golden_and_oracle(tg):
     out2 = pp.func_laplacian_transformation(pp.func_make_symmetric(A2, N2, T2), N2, T2)
     assert torch.equal(out2._indices().cpu(), torch.from_numpy(ni))
     np.testing.assert_allclose(out2._values().cpu().numpy(), nv, rtol=1e-13, atol=0)
+
+
+# --------------------------------------------------------------------------
+# degenerate shapes through every stage of the path
+# --------------------------------------------------------------------------
+def test_degenerate_inputs(tg):
+    """empty tensors, a single node / slice, band 1, no edges, odd feature widths: every stage returns the
+    right shapes and the oracle's numbers instead of tripping over a zero-sized launch"""
+    from tmgcn_b200 import ops
+    dev = "cuda"
+    # (a) empty sparse tensor, and T = N = 1
+    M3 = tg.create_matrix_M(3, 2)
+    empty = torch.sparse_coo_tensor(torch.zeros(3, 0, dtype=torch.int64), torch.zeros(0, dtype=torch.float64), (3, 4, 4))
+    out = tg.func_MProduct(empty.coalesce(), M3, no_diag=2)
+    assert out._nnz() == 0 and tuple(out.shape) == (3, 4, 4)
+    one = torch.sparse_coo_tensor(torch.zeros(3, 1, dtype=torch.int64), torch.tensor([2.5], dtype=torch.float64), (1, 1, 1))
+    out = tg.func_MProduct(one.coalesce(), tg.create_matrix_M(1, 1), no_diag=1)
+    assert out._nnz() == 1 and float(out._values()[0]) == 2.5
+    # (b) stencil with b = 1 is the identity scaled by the diagonal; T = 1
+    x = torch.randn(1, 5, 3, device=dev)
+    y = ops.stencil_fwd(x, tg.Band(tg.create_matrix_M(1, 1)))
+    assert torch.equal(y, x)
+    # (d) SpMM over an all-empty CSR and odd widths (F = 1, 3, 6: the scalar / float2 paths)
+    T, N = 2, 6
+    csr0 = tg.SliceCSR.from_coo(torch.zeros(3, 0, dtype=torch.int64), torch.zeros(0), T, N)
+    for F in (1, 3, 6):
+        X = torch.randn(T, N, F, device=dev)
+        assert torch.count_nonzero(ops.spmm_raw(csr0, X)) == 0
+        idx = torch.tensor([[0, 0, 1, 1, 1], [0, 5, 2, 2, 3], [1, 5, 0, 4, 3]])
+        val = torch.tensor([1.0, -2.0, 0.5, 4.0, 3.0])
+        csr = tg.SliceCSR.from_coo(idx, val, T, N)
+        ref = torch.zeros(T, N, F, dtype=torch.float64)
+        for (t, i, j), v in zip(idx.t().tolist(), val.tolist()):
+            ref[t, i] += v * X[t, j].double().cpu()
+        assert relerr(ops.spmm_raw(csr, X), ref) < 1e-6
+    # (c) GEMM with zero rows and a 1 x 1 weight
+    W = torch.randn(3, 2, device=dev)
+    assert tuple(ops.gemm_xw(torch.zeros(0, 4, 3, device=dev), W).shape) == (0, 4, 2)
+    assert relerr(ops.gemm_xw(torch.full((1, 1, 1), 3.0, device=dev), torch.full((1, 1), -2.0, device=dev)),
+                  torch.full((1, 1, 1), -6.0)) < 1e-7
+    # (e) readout with no edges: empty logits, zero gradients of the right shapes
+    Y = torch.randn(2, 6, 4, device=dev, requires_grad=True)
+    U = torch.randn(8, 2, device=dev, requires_grad=True)
+    plan = tg.EdgePlan(torch.zeros(3, 0, dtype=torch.int64), 6)
+    logits = ops.edge_readout(Y, U, plan)
+    assert tuple(logits.shape) == (0, 2)
+    logits.sum().backward()
+    assert torch.count_nonzero(Y.grad) == 0 and torch.count_nonzero(U.grad) == 0
+    # a model on a graph whose first and last slices are empty
+    idx = torch.tensor([[1, 1, 2], [0, 3, 2], [3, 0, 2]])
+    At = tg.SliceCSR.from_coo(idx, torch.tensor([0.5, 0.5, 1.0]), 4, 5)
+    X = torch.randn(4, 5, 2)
+    edges = torch.tensor([[0, 1, 3], [0, 3, 4], [1, 0, 4]])
+    torch.manual_seed(3)
+    gcn = tg.EmbeddingGCN(At, X, edges, tg.create_matrix_M(4, 2), hidden_feat=[3, 2], condensed_W=True, use_Minv=False)
+    out = gcn()
+    assert tuple(out.shape) == (3, 2) and torch.isfinite(out).all()
+    assert torch.count_nonzero(out[2]) == 0          # node 4 has no entry in slices 2 and 3 (band 2)

@@ -688,7 +688,8 @@ int tmgcn_edge_class_sums(const float *dout, const int64_t *inc_ptr, const int64
     TMGCN_REQUIRE(n_rows >= 0, "edge_class_sums: bad sizes");
     TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_class_sums: C=%d outside [1, %d]", C, MAXC);
     if (n_rows == 0) return 0;
-    TMGCN_REQUIRE(dout && inc_ptr && S, "edge_class_sums: null pointer");
+    // dout / perm may be null when no edge touches any row (E = 0): the kernel then never dereferences them
+    TMGCN_REQUIRE(inc_ptr && S, "edge_class_sums: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned g = (unsigned)ceil_div(n_rows, 256);
     if (C <= 2) row_class_sums_kernel<2><<<g, 256, 0, st>>>(dout, inc_ptr, perm, n_rows, S, C);
