@@ -80,7 +80,7 @@ def _worker(rank, world, port, T, N, F, b, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,T,b", [(2, 12, 4), (3, 14, 3), (2, 40, 20)])
+@pytest.mark.parametrize("world,T,b", [(2, 12, 4), (3, 14, 3), (2, 40, 20), (4, 36, 10)])
 def test_time_sharding_gloo(world, T, b):
     mgr = mp.Manager()
     ret = mgr.dict()
