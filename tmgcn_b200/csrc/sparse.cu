@@ -534,6 +534,195 @@ __global__ void __launch_bounds__(32) merge_rows_staged(const int64_t *__restric
     }
 }
 
+// Time-tiled fill (opt-in: TMGCN_MERGE_TT=1; fp32 values, b <= 12).  TT = 4 consecutive output slices of the
+// same 32 rows share B-1 of their B source slices, so ONE merge over the NS = B-1+TT sources feeds all four:
+// a step takes the smallest pending column, every cursor sitting on it hands over its value, and output tt
+// (whose window is slots tt .. tt+B-1) accumulates its own fp64 chain over its slots in ascending slice order
+// -- bit for bit what the single-output kernels produce -- and is emitted iff one of its slots with a
+// non-zero weight was hit.  Per output that is ~55 instructions instead of ~97, and the segments are staged
+// once for four outputs.  Staging is a pool (segments packed back to back), not B fixed-size buffers.
+template <int B, int TT>
+__global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict__ in_rowptr,
+                                                       const int32_t *__restrict__ in_col,
+                                                       const float *__restrict__ in_val, int T_out, int halo,
+                                                       int64_t N, const double *__restrict__ band_w, int b,
+                                                       int pool, const int64_t *__restrict__ out_rowptr,
+                                                       int32_t *__restrict__ out_col, float *__restrict__ out_val) {
+    constexpr int NS = B - 1 + TT;
+    extern __shared__ __align__(16) uint8_t stage_raw[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_raw);   // `pool` entries of {col, val}
+    const int lane = threadIdx.x;
+    const int64_t nblk = (N + 31) / 32;
+    const int n_groups = (T_out + TT - 1) / TT;
+    const int64_t n_tasks = (int64_t)n_groups * nblk;
+    for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const int g = (int)(task / nblk);
+        const int t0 = g * TT;
+        const int64_t i = (task - (int64_t)g * nblk) * 32 + lane;
+        const bool live = i < N;
+        const int64_t ic = live ? i : N - 1;
+        // weights of output tt on slot k (lag l = B-1-k+tt), zero outside its window / the band / the tensor
+        double w[TT][B];
+        uint32_t nz[TT];                         // slots whose weight for output tt is non-zero
+        bool used[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) used[k] = false;
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) {
+            nz[tt] = 0;
+#pragma unroll
+            for (int j = 0; j < B; ++j) {        // j-th slot of the window: slot k = tt + j, lag l = B-1-j
+                const int l = B - 1 - j;
+                const int sl = halo + t0 + tt - l;
+                double wl = 0.0;
+                if (l < b && t0 + tt < T_out && sl >= 0) wl = band_w[(int64_t)(t0 + tt) * b + l];
+                w[tt][j] = wl;
+                if (wl != 0.0) {
+                    nz[tt] |= 1u << (tt + j);
+                    used[tt + j] = true;
+                }
+            }
+        }
+        // row pointers of the used slots
+        int64_t p0s[NS], p1s[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            p0s[k] = p1s[k] = 0;
+            if (used[k]) {                       // warp-uniform
+                const int sl = halo + t0 - (B - 1) + k;
+                p0s[k] = in_rowptr[(int64_t)sl * N + ic];
+                p1s[k] = in_rowptr[(int64_t)sl * N + ic + 1];
+            }
+            if (!live) p0s[k] = p1s[k];
+        }
+        // pack the segments back to back; all copies in flight together
+        int64_t seg0s[NS];
+        int32_t off[NS + 1];
+        off[0] = 0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            seg0s[k] = __shfl_sync(0xffffffffu, p0s[k], 0);
+            const int64_t seg1 = __shfl_sync(0xffffffffu, p1s[k], 31);
+            const int64_t len = seg1 - seg0s[k];
+            off[k + 1] = off[k] + (int32_t)(len > (int64_t)pool ? pool + 1 : len);
+        }
+        const bool fits = off[NS] <= pool;       // warp-uniform
+        if (fits) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int len = off[k + 1] - off[k];
+                uint32_t dst = sbase + (uint32_t)(off[k] + lane) * 8;
+                for (int q = lane; q < len; q += 32, dst += 32 * 8) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(in_col + seg0s[k] + q)
+                                 : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4), "l"(in_val + seg0s[k] + q)
+                                 : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        int32_t *oc[TT];
+        float *ov[TT];
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) {
+            const int64_t ob = (live && t0 + tt < T_out) ? out_rowptr[(int64_t)(t0 + tt) * N + i] : 0;
+            oc[tt] = out_col + ob;
+            ov[tt] = out_val + ob;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (fits) {
+            uint32_t p[NS], e[NS];
+            int32_t cur[NS];
+            int32_t v[NS];
+            double unused = 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                p[k] = sbase + (uint32_t)(off[k] + (int32_t)(p0s[k] - seg0s[k])) * 8;
+                e[k] = p[k] + (uint32_t)(p1s[k] - p0s[k]) * 8;
+                v[k] = 0;
+                cur[k] = -2;
+                cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], -1, 0.0, unused);
+            }
+            while (true) {
+                int m = cur[0];
+#pragma unroll
+                for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
+                if (m == INT_MAX) break;
+                uint32_t hits = 0;
+                double vd[NS];
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const bool hit = cur[k] == m;
+                    hits |= hit ? (1u << k) : 0u;
+                    vd[k] = hit ? (double)__int_as_float(v[k]) : 0.0;      // +0 leaves a chain unchanged
+                }
+#pragma unroll
+                for (int tt = 0; tt < TT; ++tt) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < B; ++j) acc = fma(w[tt][j], vd[tt + j], acc);
+                    if (hits & nz[tt]) {
+                        *oc[tt] = m;
+                        *ov[tt] = (float)acc;
+                        ++oc[tt];
+                        ++ov[tt];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NS; ++k) cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
+            }
+        } else {
+            // hub blocks: the same merge on global memory
+            int64_t gp[NS], ge[NS];
+            int32_t cur[NS];
+            float v[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                gp[k] = p0s[k];
+                ge[k] = p1s[k];
+                const bool in = gp[k] < ge[k];
+                cur[k] = in ? in_col[gp[k]] : INT_MAX;
+                v[k] = in ? in_val[gp[k]] : 0.f;
+            }
+            while (true) {
+                int m = cur[0];
+#pragma unroll
+                for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
+                if (m == INT_MAX) break;
+                uint32_t hits = 0;
+                double vd[NS];
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const bool hit = cur[k] == m;
+                    hits |= hit ? (1u << k) : 0u;
+                    vd[k] = hit ? (double)v[k] : 0.0;
+                    gp[k] += hit ? 1 : 0;
+                }
+#pragma unroll
+                for (int tt = 0; tt < TT; ++tt) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < B; ++j) acc = fma(w[tt][j], vd[tt + j], acc);
+                    if (hits & nz[tt]) {
+                        *oc[tt] = m;
+                        *ov[tt] = (float)acc;
+                        ++oc[tt];
+                        ++ov[tt];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const bool in = gp[k] < ge[k];
+                    cur[k] = in ? in_col[gp[k]] : INT_MAX;
+                    v[k] = in ? in_val[gp[k]] : 0.f;
+                }
+            }
+        }
+        __syncwarp();                            // the pool is reused by the next task
+    }
+}
+
 template <bool COUNT_ONLY, typename VT>
 static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const VT *in_val, int T_out, int halo,
                         int64_t N, const double *band_w, int b, int64_t *out_counts, const int64_t *out_rowptr,
@@ -583,6 +772,30 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
                     break;
                 }
             }
+        }
+    }
+    if constexpr (!COUNT_ONLY && sizeof(VT) == 4) {
+        static int tiled = -1;
+        if (tiled < 0) {
+            const char *e = getenv("TMGCN_MERGE_TT");
+            tiled = (e && e[0] == '1') ? 1 : 0;
+        }
+        if (tiled && b <= 12) {
+            const int pool = (38 * 1024) / 8;                               // entries of {col, val}
+            const size_t smem = (size_t)pool * 8;
+            const int64_t n_tasks = (int64_t)ceil_div(T_out, 4) * ceil_div(N, (int64_t)32);
+            int64_t g = (int64_t)sm_count() * (int64_t)((220 * 1024) / (smem + 1024));
+            if (g > n_tasks) g = n_tasks;
+#define TMGCN_TILED(BB)                                                                                          \
+    if (b <= BB) {                                                                                               \
+        auto kern = merge_rows_tiled<BB, 4>;                                                                     \
+        TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        kern<<<(unsigned)g, 32, smem, st>>>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b, pool,          \
+                                            out_rowptr, out_col, out_val);                                       \
+        return after_launch("merge_rows_tiled<fill>");                                                           \
+    }
+            TMGCN_TILED(2) TMGCN_TILED(4) TMGCN_TILED(6) TMGCN_TILED(8) TMGCN_TILED(10) TMGCN_TILED(12)
+#undef TMGCN_TILED
         }
     }
 #define TMGCN_MERGE_STAGED(BB, LL)                                                                               \
