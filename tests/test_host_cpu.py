@@ -150,3 +150,33 @@ def test_committed_bench_profile_has_the_contract_keys():
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["vs_baseline"] is None                      # BASELINE.md holds no published number for this metric
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tmgcn.h is the FFI contract: it must compile as C99 (and C++) on its own, and a C program linked
+    against the shared library must resolve the symbols it declares (no GPU needed to call the version query)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "tmgcn.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %lld\\n", tmgcn_abi_version(), (long long)tmgcn_launch_count());\n'
+                   '  return tmgcn_abi_version() == TMGCN_ABI_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                   check=True)
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)],
+                       check=True)
+    from tmgcn_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ltmgcn_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["1", "0"], (r.stdout, r.stderr)
