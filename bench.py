@@ -1,16 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the TM-GCN propagation hot path on B200 (bench contract: see README / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--preset NAME] [--no-extras]
 
-A "step" = one TM-GCN layer forward + backward (dense M-transform stencil, facewise
-SpMM, feature GEMM, edge readout + classifier, and the backward of all of them) over
-one shard of the synthetic dynamic graph.  Metric: slice-edges/s = sum_t nnz(A~_t)
-processed per second, whole job.  Workload = BASELINE.json configs[4] cut to what one
-GPU holds: N = 2M nodes, ~22M stored entries per input slice, b = 10, F = 128 -> 128,
-T = 32 slices per GPU (T = 256 over 8 GPUs, weak scaling), rho = 0.9.
+A "step" = one TM-GCN layer forward + backward (dense M-transform stencil, facewise SpMM, feature GEMM,
+edge readout + classifier, and the backward of all of them) over one shard of the synthetic dynamic
+graph.  Metric: slice-edges/s = sum_t nnz(A~_t) processed per second, whole job.
+
+Workloads (`--preset`; every field can be overridden on the command line):
+  c5shard (default)  BASELINE.json configs[4] cut to what one GPU holds: N = 2M nodes, ~22M stored entries per
+                     input slice, b = 10, F = 128 -> 128, T = 32 slices per GPU (T = 256 over 8 GPUs): WEAK scaling
+  c5cut              a fits-one-GPU cut of configs[4] with the total work fixed: N = 500k, m = 2.5M, T = 128,
+                     b = 10 (T/G = 16 >= b-1 at 8 GPUs): STRONG scaling
+  c4                 configs[3], Reddit shape: N = 55 863, T = 178, b = 20, F = 128: STRONG scaling
+  c1f128             configs[0] shape at F = 128 (N = 5 881, T = 95, b = 20): small enough for the reference's
+                     CPU path to run the WHOLE config, so both arms measure the same thing
+The default invocation times c5shard (the headline line) and then, with fewer steps, c5cut and c4
+(`strong_scaling`), c1f128 against the CPU port on the same data (`same_config`, N = 1 only) and, at N > 1,
+a sharded-vs-unsharded numerical check (`parity_multi_gpu`) before any timing.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -29,6 +39,18 @@ os.dup2(2, 1)
 import torch  # noqa: E402
 
 SEED = 20261017
+METRIC = "TM-GCN layer fwd+bwd slice-edges/s"
+
+PRESETS = {
+    "c5shard": dict(nodes=2_000_000, pairs=10_000_000, rho=0.9, band=10, feat=128, classes=2, slices=32,
+                    scaling="weak", label="configs[4] shard"),
+    "c5cut": dict(nodes=500_000, pairs=2_500_000, rho=0.9, band=10, feat=128, classes=2, total_slices=128,
+                  scaling="strong", label="configs[4] cut to fit one GPU (fixed total work)"),
+    "c4": dict(nodes=55_863, pairs=32_000, rho=0.9, band=20, feat=128, classes=2, total_slices=178,
+               scaling="strong", label="configs[3] Reddit shape"),
+    "c1f128": dict(nodes=5_881, pairs=2_580, rho=0.9, band=20, feat=128, classes=2, total_slices=95,
+                   scaling="strong", label="configs[0] Bitcoin-OTC shape at F=128", host_data=True),
+}
 
 
 def parse():
@@ -37,39 +59,62 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nodes", type=int, default=2_000_000)
-    ap.add_argument("--slices", type=int, default=32, help="time slices per GPU")
-    ap.add_argument("--pairs", type=int, default=10_000_000, help="undirected pairs per slice (m)")
-    ap.add_argument("--rho", type=float, default=0.9)
-    ap.add_argument("--band", type=int, default=10)
-    ap.add_argument("--feat", type=int, default=128)
-    ap.add_argument("--classes", type=int, default=2)
+    ap.add_argument("--preset", default="c5shard", choices=sorted(PRESETS))
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
+    ap.add_argument("--nodes", type=int, default=None)
+    ap.add_argument("--slices", type=int, default=None, help="time slices per GPU (weak scaling)")
+    ap.add_argument("--total-slices", type=int, default=None, help="time slices of the whole tensor (strong scaling)")
+    ap.add_argument("--pairs", type=int, default=None, help="undirected pairs per slice (m)")
+    ap.add_argument("--rho", type=float, default=None)
+    ap.add_argument("--band", type=int, default=None)
+    ap.add_argument("--feat", type=int, default=None)
+    ap.add_argument("--classes", type=int, default=None)
     ap.add_argument("--act", default="none")
     ap.add_argument("--bwd", default="auto", choices=["auto", "dense", "lowrank"],
                     help="backward formulation (auto = low-rank when the layer is linear, see layer_step.py)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU forward halo: fused into the stencil over NVLink peer memory, or NCCL send/recv")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="time only the selected workload (no strong_scaling / same_config / parity legs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-nodes", type=int, default=100_000, help="bounded CPU sample: nodes")
-    ap.add_argument("--cpu-slices", type=int, default=8)
+    ap.add_argument("--cpu-nodes", type=int, default=50_000, help="bounded CPU sample: nodes")
+    ap.add_argument("--cpu-slices", type=int, default=8, help="bounded CPU sample: slices")
     return ap.parse_args()
 
 
-def measured_traffic(args, T_local):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very config
-    (profiles/r01_traffic.json), or None when the config differs."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        d = json.load(open(p))
-        c = d["config"]
-        same = (c["nodes"] == args.nodes and c["slices"] == T_local and c["pairs"] == args.pairs
-                and abs(c["rho"] - args.rho) < 1e-12 and c["band"] == args.band and c["feat"] == args.feat)
-        for k, v in d["kernels"].items():
-            if same and k.startswith("void spmm_rows<4, 32, 0"):
-                return v["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    return None
+def resolve_workload(args, preset=None, cli=True):
+    """preset (+ explicit command-line overrides) -> workload dict"""
+    wl = dict(PRESETS[preset or args.preset])
+    wl["name"] = preset or args.preset
+    if cli:
+        for k in ("nodes", "pairs", "rho", "band", "feat", "classes", "slices", "scaling"):
+            v = getattr(args, k)
+            if v is not None:
+                wl[k] = v
+        if args.total_slices is not None:
+            wl["total_slices"] = args.total_slices
+    wl["act"] = args.act
+    if wl["scaling"] == "weak" and "slices" not in wl:
+        wl["slices"] = wl.pop("total_slices")
+    if wl["scaling"] == "strong" and "total_slices" not in wl:
+        wl["total_slices"] = wl.pop("slices")
+    return wl
+
+
+def describe(wl, T_total, world, blocks=None, flush=False):
+    N, m = wl["nodes"], wl["pairs"]
+    shard = (f"T={wl['slices']}/GPU (T={T_total} total, weak scaling)" if wl["scaling"] == "weak" else
+             f"T={T_total} total over {world} GPU(s) (strong scaling: fixed total work)")
+    d = {"workload": f"{wl['label']} [{wl['name']}]: synthetic dynamic graph N={N}, m={m} pairs/slice "
+                     f"(~{2 * m + N} stored entries/input slice), rho={wl['rho']}, b={wl['band']}, "
+                     f"F={wl['feat']}->{wl['feat']}, C={wl['classes']}, {shard}, time-sharded in nnz-balanced "
+                     f"contiguous blocks, E=m*T/8 readout edges, act={wl['act']}",
+         "l2_policy": "L2 flushed between timed steps (a 256 MB buffer is rewritten before every step)" if flush else
+                      "inputs exceed L2 (every stage streams several times the 126 MB L2 per step)",
+         "seed": SEED}
+    if blocks is not None:
+        d["time_blocks"] = [list(x) for x in blocks]
+    return d
 
 
 def peaks():
@@ -78,6 +123,26 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(wl, T_own, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very config
+    (profiles/r02_traffic.json, else r01), or None when the config differs."""
+    if world != 1:
+        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            c = d["config"]
+            same = (c["nodes"] == wl["nodes"] and c["slices"] == T_own and c["pairs"] == wl["pairs"]
+                    and abs(c["rho"] - wl["rho"]) < 1e-12 and c["band"] == wl["band"] and c["feat"] == wl["feat"]
+                    and c.get("generator", "chain") == "global")
+            for k, v in d["kernels"].items():
+                if same and k.startswith("void spmm_rows<4, 32, 0"):
+                    return v["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    return None
 
 
 class ClockSampler:
@@ -118,7 +183,6 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        # median over the samples taken under load (upper half: idle samples sit at the low end)
         med = sm[len(sm) // 2] if sm else None
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -127,14 +191,15 @@ class ClockSampler:
 # CPU arm: the oracle port of the reference path (reference-as-is structure: fp64
 # M-transform + per-slice sparse.mm into an fp32 buffer, autograd backward)
 # ----------------------------------------------------------------------------------
-def cpu_sample(args, steps=1, warmup=0):
+def cpu_run(wl, N, T, m, steps, warmup, what):
+    """`steps` timed + `warmup` untimed layer fwd+bwd steps of the CPU port on an (N, T, m) graph with the
+    workload's density / band / widths.  Returns the measurement with the configuration it REALLY ran."""
     import oracle
     from tmgcn_b200 import synth
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    N, T, b, F, C = args.cpu_nodes, args.cpu_slices, args.band, args.feat, args.classes
-    m = max(int(args.pairs * (N / args.nodes)), 1)
-    idx, val = synth.synth_coo(N, T, m, args.rho, seed=SEED, device="cpu")
+    b, F, C = wl["band"], wl["feat"], wl["classes"]
+    idx, val = synth.synth_coo(N, T, m, wl["rho"], seed=SEED, device="cpu")
     M = oracle.create_matrix_M(T, b)
     t_mp = time.perf_counter()
     ai, av = oracle.func_MProduct(idx.numpy(), val.numpy(), (T, N, N), M.numpy())
@@ -145,22 +210,35 @@ def cpu_sample(args, steps=1, warmup=0):
     H = torch.rand(T, N, F, generator=g)
     W = torch.randn(F, F, generator=g) / F ** 0.5
     U = torch.randn(2 * F, C, generator=g)
-    E = m * T // 8
+    E = max(m * T // 8, 1)
     pick = torch.sort(torch.randint(0, nnz, (E,), generator=g)).values
     edges = torch.from_numpy(ai[:, pick.numpy()])
     dOut = torch.randn(E, C, generator=g)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        oracle.layer_fwd_bwd(At, H, M, W, U, edges, dOut, args.act, as_reference=True)
+        oracle.layer_fwd_bwd(At, H, M, W, U, edges, dOut, wl["act"], as_reference=True)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     sec = sum(times) / len(times)
     return {"value": nnz / sec, "unit": "slice-edges/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port of ehf:307-312,342-355 + autograd backward (reference-as-is slice-assign loop), "
-                      f"N={N} T={T} m={m} rho={args.rho} b={b} F={F}: {nnz} slice-edges, {sec:.2f} s/step",
-            "seconds_per_step": sec, "slice_edges": nnz, "mtransform_sparse_s": t_mp}
+            "sample": f"{what}: oracle port of ehf:307-312,342-355 + autograd backward (reference-as-is slice-assign "
+                      f"loop), N={N} T={T} m={m} rho={wl['rho']} b={b} F={F} C={C}: {nnz} slice-edges, "
+                      f"{sec:.2f} s/step over {len(times)} timed step(s)",
+            "seconds_per_step": sec, "steps_run": len(times), "warmup_run": warmup, "slice_edges": nnz,
+            "mtransform_sparse_s": t_mp, "ran": {"nodes": N, "slices": T, "pairs": m, "edges": E}}
+
+
+def cpu_sample_shape(args, wl):
+    """what the CPU arm runs for this workload: the whole thing when it is small enough (host_data presets),
+    else a bounded sample of the same density / band / widths"""
+    T_total = wl.get("total_slices", wl.get("slices"))
+    if wl.get("host_data"):
+        return wl["nodes"], T_total, wl["pairs"], True
+    N = min(args.cpu_nodes, wl["nodes"])
+    T = min(args.cpu_slices, T_total)
+    return N, T, max(int(wl["pairs"] * (N / wl["nodes"])), 1), False
 
 
 def run_reference(args):
@@ -168,13 +246,25 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    r = cpu_sample(args, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup else 0)
+    wl = resolve_workload(args)
+    N, T, m, whole = cpu_sample_shape(args, wl)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    r = cpu_run(wl, N, T, m, steps, warmup,
+                "the whole workload" if whole else "bounded sample of the workload (same density, band and widths)")
+    T_total = wl.get("total_slices", wl.get("slices", 0) * max(1, args.gpus))
+    cfg = {"workload": f"CPU arm ran N={N}, T={T}, m={m} pairs/slice, rho={wl['rho']}, b={wl['band']}, "
+                       f"F={wl['feat']}->{wl['feat']}, C={wl['classes']}, E={r['ran']['edges']} readout edges, "
+                       f"act={wl['act']} on {r['cores']} host cores"
+                       + ("" if whole else f" -- a bounded sample of [{wl['name']}] (the GPU arm's N={wl['nodes']}, "
+                                           f"m={wl['pairs']}, T={T_total}); its rate is an extrapolation, not a "
+                                           f"same-config measurement"),
+           "sample_of": describe(wl, T_total, max(1, args.gpus))["workload"], "same_config_as_gpu_arm": whole,
+           "extrapolated": not whole, "seed": SEED}
     line = {
-        "impl": "reference", "metric": "TM-GCN layer fwd+bwd slice-edges/s", "value": r["value"],
-        "unit": "slice-edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64/f32 (reference dtypes)", "data": "synthetic",
-        "config": workload_name(args),
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "slice-edges/s", "n_gpus": args.gpus,
+        "steps": r["steps_run"], "warmup": r["warmup_run"], "ms_per_step": r["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+        "dtype": "f64/f32 (reference dtypes)", "data": "synthetic", "config": cfg,
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "slice-edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -182,98 +272,163 @@ def run_reference(args):
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
-def workload_name(args, T_local=None):
-    T_local = args.slices if T_local is None else T_local
-    return {"workload": f"configs[4] shard: synthetic dynamic graph N={args.nodes}, m={args.pairs} pairs/slice "
-                        f"(~{2 * args.pairs + args.nodes} stored entries/input slice), rho={args.rho}, b={args.band}, "
-                        f"F={args.feat}->{args.feat}, C={args.classes}, T={T_local}/GPU "
-                        f"(T={T_local * args.gpus} total, time-sharded), E=m*T/8 readout edges, act={args.act}",
-            "l2_policy": "inputs exceed L2 (each stage streams >= 1 GB per slice; 126 MB L2)",
-            "seed": SEED}
-
-
 # ----------------------------------------------------------------------------------
 # CUDA arm
 # ----------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
+class Ctx:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.args = args
+        self.peer_storage = None          # one symmetric allocation shared by every workload of the run
+        self.halo_mode = "none" if self.world == 1 else args.halo
+        self.l2 = torch.cuda.get_device_properties(self.dev).L2_cache_size
+        self.flush_buf = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_min(self, v):
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.dev, dtype=torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return int(t.item())
+
+    def ensure_peer_storage(self, numel):
+        """symmetric memory for the layer input of every workload (allocated once, sized for the largest)"""
+        from tmgcn_b200 import sharding
+        if self.world == 1 or self.halo_mode != "peer":
+            return
+        if self.peer_storage is not None and self.peer_storage[0].numel() >= numel:
+            return
+        ok = 1
+        try:
+            self.peer_storage = sharding.PeerHalo.allocate(numel, self.dev)
+        except Exception as ex:  # pragma: no cover - depends on the box
+            print(f"[bench] symmetric memory unavailable ({ex}); falling back to the NCCL halo", file=sys.stderr)
+            ok = 0
+        if self.all_min(ok) == 0:
+            self.peer_storage, self.halo_mode = None, "nccl"
+
+    def flush_l2(self):
+        if self.flush_buf is None:
+            self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.flush_buf.fill_(1)
+
+
+def plan_blocks(wl, ctx):
+    """-> (T_total, blocks) with nnz-balanced contiguous time blocks; shrinks a weak-scaling shard that
+    does not fit this GPU (all ranks agree)."""
+    from tmgcn_b200 import sharding
+    N, b, F, m, rho = wl["nodes"], wl["band"], wl["feat"], wl["pairs"], wl["rho"]
+    world, rank = ctx.world, ctx.rank
+    free, _ = torch.cuda.mem_get_info()
+    est_nnz_t = (2 * m + N) * (1 + (b - 1) * (1 - rho) * 1.05)
+
+    def blocks_for(T_total):
+        w = sharding.slice_weight_estimate(T_total, b, N, m, rho)
+        return sharding.balanced_bounds(w, world) if world > 1 else [(0, T_total)]
+
+    def need(Tl, halo):
+        # steady state: H + three work buffers, A~ and its transpose, edge ids + incidence list
+        dense = 4.0 * N * F * (4 * Tl + 2 * halo)
+        sparse = 2 * (est_nnz_t * Tl * 8 + 8.0 * N * Tl)
+        edges = m * Tl / 8 * (16 + 16 + 24)
+        return dense + sparse + edges + 4e9
+
+    if wl["scaling"] == "weak":
+        per = wl["slices"]
+        while True:
+            T_total = per * world
+            blocks = blocks_for(T_total)
+            t0, t1 = blocks[rank]
+            fits = 1 if (need(t1 - t0, (b - 1) if rank > 0 else 0) <= 0.97 * free or per <= b) else 0
+            if ctx.all_min(fits):
+                break
+            per //= 2
+        wl["slices"] = per
+    else:
+        T_total = wl["total_slices"]
+        blocks = blocks_for(T_total)
+        t0, t1 = blocks[rank]
+        if not ctx.all_min(1 if need(t1 - t0, (b - 1) if rank > 0 else 0) <= 0.97 * free else 0):
+            raise RuntimeError(f"workload [{wl['name']}] does not fit {world} GPU(s)")
+    return T_total, blocks
+
+
+def run_workload(wl, ctx, steps, warmup, full):
+    """Build the shard of workload `wl` this rank owns, time `steps` layer steps (max over ranks) and return the
+    measurements.  full = True adds the e2e timing, the clock sampler and the stage-(a) timing (headline line)."""
     import tmgcn_b200 as tg
     from tmgcn_b200 import _lib, ops, sharding, synth
     from tmgcn_b200.layer_step import LayerStep
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load(build_if_missing=False)
-
-    N, b, F, C = args.nodes, args.band, args.feat, args.classes
-    T_local = args.slices
+    dist, world, rank, dev = ctx.dist, ctx.world, ctx.rank, ctx.dev
+    N, b, F, C, m, rho = wl["nodes"], wl["band"], wl["feat"], wl["classes"], wl["pairs"], wl["rho"]
+    T_total, blocks = plan_blocks(wl, ctx)
+    t0, t1 = blocks[rank]
+    T_own = t1 - t0
     halo = (b - 1) if rank > 0 else 0
-
-    # ---- memory plan: 3 work buffers + H (+halo) + A~ and its transpose + inputs ----
-    free, total = torch.cuda.mem_get_info()
-    est_nnz_t = (2 * args.pairs + N) * (1 + (b - 1) * (1 - args.rho) * 1.05)
-
-    def need(Tl):
-        # steady state: H + three work buffers, A~ and its transpose, edge ids + incidence list
-        # (the input tensor and the transpose scratch are freed before the dense buffers exist)
-        dense = 4.0 * N * F * (4 * Tl + 2 * halo)
-        sparse = 2 * (est_nnz_t * Tl * 8 + 8.0 * N * Tl)
-        edges = args.pairs * Tl / 8 * (16 + 16 + 24)
-        return dense + sparse + edges + 4e9
-    while T_local > b and need(T_local) > 0.97 * free:
-        T_local //= 2
     if world > 1:
-        tl = torch.tensor([T_local], device=dev)
-        dist.all_reduce(tl, op=dist.ReduceOp.MIN)
-        T_local = int(tl.item())
-    T_total = T_local * world
-    t0, t1 = rank * T_local, (rank + 1) * T_local
+        sharding.assert_single_hop(T_own, b - 1, world, dev)
+    flush = 4.0 * N * F * T_own <= 4 * ctx.l2          # small workloads would otherwise be timed out of L2
 
-    # ---- inputs (setup, untimed) ----
+    # ---- inputs (setup, untimed): this rank's window of ONE global dynamic graph -------------------------
     M = tg.create_matrix_M(T_total, b)
     band = tg.Band(M)
-    A_own = synth.synth_csr(N, T_local, args.pairs, args.rho, seed=SEED + rank)
+    if wl.get("host_data"):      # small config: the legacy seeded chain on the CPU, the same data the CPU arm uses
+        idx, val = synth.synth_coo(N, T_total, m, rho, seed=SEED, device="cpu")
+        sel = (idx[0] >= t0) & (idx[0] < t1)
+        own = idx[:, sel].clone()
+        own[0] -= t0
+        A_own = tg.SliceCSR.from_coo(own, val[sel], T_own, N)
+        del idx, val, own, sel
+    else:
+        A_own = synth.synth_csr(N, T_own, m, rho, seed=SEED, t_start=t0)
     A_in = sharding.exchange_sparse_halo(A_own, halo_out=b - 1, rank=rank, world=world) if world > 1 else A_own
     At = ops.mtransform_sparse(A_in, band, t0, t1, halo)          # cold run (also the one the bench uses)
     torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_tr = float("inf")
-    for _ in range(2):   # warm runs, timed on the device: plan, scan, fill.  The first one may pay a cudaMalloc of
-        ev0.record()     # the 10 GB output inside the region; the second reuses the block the first one freed.
-        At2 = ops.mtransform_sparse(A_in, band, t0, t1, halo)
-        ev1.record()
-        torch.cuda.synchronize()
-        t_tr = min(t_tr, ev0.elapsed_time(ev1) * 1e-3)
-        assert torch.equal(At2.rowptr, At.rowptr) and torch.equal(At2.col, At.col) and torch.equal(At2.val, At.val)
-        del At2
+    t_tr, tr_bytes = None, None
     nnz_in = A_in.nnz
-    tr_bytes = 8.0 * nnz_in + 4.0 * (N + 1) * (T_local + halo) + 8.0 * At.nnz + 4.0 * (N + 1) * T_local
+    if full:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_tr = float("inf")
+        for _ in range(2):   # warm runs, timed on the device: plan, scan, fill.  The first one may pay a cudaMalloc
+            ev0.record()     # of the output inside the region; the second reuses the block the first one freed.
+            At2 = ops.mtransform_sparse(A_in, band, t0, t1, halo)
+            ev1.record()
+            torch.cuda.synchronize()
+            t_tr = min(t_tr, ev0.elapsed_time(ev1) * 1e-3)
+            assert torch.equal(At2.rowptr, At.rowptr) and torch.equal(At2.col, At.col) and torch.equal(At2.val, At.val)
+            del At2
+        tr_bytes = 8.0 * nnz_in + 4.0 * (N + 1) * (T_own + halo) + 8.0 * At.nnz + 4.0 * (N + 1) * T_own
     del A_own, A_in
     torch.cuda.empty_cache()
-    E = args.pairs * T_local // 8
+    E = max(m * T_own // 8, 1)
     edges = synth.synth_edges(At, E, seed=SEED + rank)
-    plan = tg.EdgePlan(edges, N)
+    plan = tg.EdgePlan(edges, N, T=T_own)
     del edges
-    step = LayerStep(At, band, plan, F, F, C, args.act, t0, t1, halo, bwd_mode=args.bwd)
+    step = LayerStep(At, band, plan, F, F, C, wl["act"], t0, t1, halo, bwd_mode=ctx.args.bwd)
     torch.cuda.empty_cache()
     gen = torch.Generator(device=dev).manual_seed(SEED + 100 + rank)
-    peer, halo_mode = None, ("none" if world == 1 else args.halo)
-    if world > 1 and args.halo == "peer":
-        try:        # layer input in symmetric memory: the boundary stencil reads the predecessor's HBM over NVLink
-            peer = sharding.PeerHalo(T_local, N, F, b - 1, rank, world, dev)
-        except Exception as ex:  # pragma: no cover - depends on the box
-            print(f"[bench] symmetric memory unavailable ({ex}); falling back to the NCCL halo", file=sys.stderr)
-            halo_mode = "nccl"
-        ok = torch.tensor([1 if peer is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            peer, halo_mode = None, "nccl"
-    H = peer.H if peer is not None else torch.empty(T_local + halo, N, F, device=dev)
+    peer, halo_mode = None, ctx.halo_mode
+    if world > 1 and halo_mode == "peer":
+        tmax = max(x1 - x0 for x0, x1 in blocks)
+        ctx.ensure_peer_storage(tmax * N * F)
+        halo_mode = ctx.halo_mode
+        if halo_mode == "peer":
+            peer = sharding.PeerHalo(T_own, N, F, b - 1, rank, world, dev, storage=ctx.peer_storage)
+    h_in = 0 if peer is not None else halo
+    H = peer.H if peer is not None else torch.empty(T_own + h_in, N, F, device=dev)
     for t in range(H.shape[0]):
         H[t].copy_(torch.rand(N, F, generator=gen, device=dev))
     gw = torch.Generator().manual_seed(SEED)
@@ -284,8 +439,7 @@ def run_ours(args):
     out_host = torch.empty(E, C).pin_memory()
     dW_host = torch.empty(F, F).pin_memory()
     dU_host = torch.empty(2 * F, C).pin_memory()
-    slice_edges_local = At.nnz
-    comm = sharding.ShardComm(b - 1, rank, world, dev) if world > 1 else None
+    comm = sharding.ShardComm(b - 1, rank, world, dev, T_own=T_own) if world > 1 else None
     copy_stream = torch.cuda.Stream(device=dev)
     ev_h2d, ev_fwd, ev_prev = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
@@ -316,11 +470,6 @@ def run_ours(args):
             copy_stream.synchronize()                   # the step's results are on the host
         return dH
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(K, e2e, stage_times=None):
         events = []
 
@@ -329,15 +478,29 @@ def run_ours(args):
             ev.record()
             events.append((name, ev))
         step.hook = hook if stage_times is not None else None
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
         n0 = _lib.launch_count()
-        s.record()
-        for _ in range(K):
-            one_step(e2e)
-        e.record()
-        barrier()
-        ms = s.elapsed_time(e)
+        if flush:
+            # small workload: rewrite a buffer larger than L2 before every step; each step is timed on its own
+            # pair of events so the flush stays outside the timed region
+            ms = 0.0
+            for _ in range(K):
+                ctx.flush_l2()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                one_step(e2e)
+                e.record()
+                torch.cuda.synchronize()
+                ms += s.elapsed_time(e)
+            ctx.barrier()
+        else:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(K):
+                one_step(e2e)
+            e.record()
+            ctx.barrier()
+            ms = s.elapsed_time(e)
         step.hook = None
         if stage_times is not None:
             per_step = {}
@@ -352,96 +515,213 @@ def run_ours(args):
             ms = float(tms.item())
         return ms, _lib.launch_count() - n0
 
-    for _ in range(max(args.warmup, 3)):
+    W_ = max(warmup, 3)
+    for _ in range(W_):
         one_step(False)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(ctx.local) if (rank == 0 and full) else None
     stage_times = {}
-    ms, launches = timed(args.steps, False, stage_times)
+    ms, launches = timed(steps, False, stage_times)
     clocks = sampler.stop() if sampler else None
-    one_step(True)
-    ms_e2e, _ = timed(args.steps, True)
-    ms_dense = None
-    if step.bwd_mode == "lowrank":     # for transparency also time the general (dense-gradient) backward
+    ms_e2e = None
+    if full:
+        one_step(True)
+        ms_e2e, _ = timed(steps, True)
+    alg = step.algorithmic_bytes(ctx.l2)
+    ms_dense, dense_stage_times, alg_dense = None, {}, None
+    if step.bwd_mode == "lowrank":     # the general (dense-gradient) layer of SURVEY 8(d): any activation takes it
         step.bwd_mode = "dense"
         one_step(False)
-        ms_dense, _ = timed(args.steps, False)
+        ms_dense, _ = timed(steps, False, dense_stage_times)
+        alg_dense = step.algorithmic_bytes(ctx.l2)
         step.bwd_mode = "lowrank"
 
-    stages_all = None
+    def gather_stages(st):
+        mine = {k: round(sum(v) / len(v), 3) for k, v in st.items()}
+        if world == 1:
+            return [mine]
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        return allr
+    stages_all = gather_stages(stage_times)
+    dense_stages_all = gather_stages(dense_stage_times) if ms_dense is not None else None
+    tot = torch.tensor([At.nnz, nnz_in], device=dev, dtype=torch.float64)
+    per_rank_nnz = [float(At.nnz)]
     if world > 1:
-        mine = {k: round(sum(v) / len(v), 3) for k, v in stage_times.items()}
-        stages_all = [None] * world
-        dist.all_gather_object(stages_all, mine)
-    tot = torch.tensor([slice_edges_local, nnz_in], device=dev, dtype=torch.float64)
-    if world > 1:
+        allr = [None] * world
+        dist.all_gather_object(allr, float(At.nnz))
+        per_rank_nnz = allr
         dist.all_reduce(tot)
     slice_edges, nnz_in_total = float(tot[0].item()), float(tot[1].item())
 
+    def stage_table(stages, algb):
+        out = {}
+        for k, v in stages.items():
+            out[k] = {"ms": round(v, 3), "GB/s": round(algb[k] / (v * 1e-3) / 1e9, 1) if (k in algb and v > 0) else None}
+        return out
+
+    sec = ms * 1e-3 / steps
+    res = {
+        "config": describe(wl, T_total, world, blocks, flush),
+        "scaling": wl["scaling"], "T_total": T_total, "ms_per_step": sec * 1e3, "value": slice_edges / sec,
+        "steps": steps, "warmup": W_, "slice_edges_per_step": slice_edges, "input_edges_per_step": nnz_in_total,
+        "slice_edges_per_rank": per_rank_nnz, "gpu_launches": launches, "halo_mode": halo_mode,
+        "backward_mode": step.bwd_mode, "clocks": clocks,
+        "stages": stage_table(stages_all[0], alg), "stages_ms_per_rank": stages_all if world > 1 else None,
+        "alg": alg, "layer_algorithmic_bytes": sum(alg.values()),
+        "E": E, "F": F, "C": C,
+    }
+    if ms_e2e is not None:
+        sec_e2e = ms_e2e * 1e-3 / steps
+        res["e2e"] = {"value": slice_edges / sec_e2e, "unit": "slice-edges/s",
+                      "h2d_bytes_per_step": dOut_host.numel() * 4,
+                      "d2h_bytes_per_step": (out_host.numel() + dW_host.numel() + dU_host.numel()) * 4,
+                      "ms_per_step": sec_e2e * 1e3,
+                      "what": "LayerStep.forward+backward through the C ABI; per step dOut (E x C, the host-side loss "
+                              "gradient) comes from pinned host memory and logits + dW + dU go back to the host; "
+                              "H, A~ and the edge list stay device-resident as the reference's ctor caches them "
+                              "(ehf:195-198)"}
+    if ms_dense is not None:
+        sd = ms_dense * 1e-3 / steps
+        res["dense"] = {"ms_per_step": sd * 1e3, "value": slice_edges / sd,
+                        "stages": stage_table(dense_stages_all[0], alg_dense),
+                        "stages_ms_per_rank": dense_stages_all if world > 1 else None,
+                        "layer_algorithmic_bytes": sum(alg_dense.values()), "alg": alg_dense}
+    if t_tr is not None:
+        res["mtransform_sparse"] = {"seconds": t_tr, "transform_edges_per_s": At.nnz / t_tr,
+                                    "algorithmic_bytes": tr_bytes, "GB/s": tr_bytes / t_tr / 1e9,
+                                    "note": "stage (a), rank-0 shard: count pass + scan + fill passes, best of two warm "
+                                            "runs, CUDA events (includes the host read of the output size); "
+                                            "bit-identical to the cold run"}
+    res["T_own"] = T_own
+    # release everything before the next workload
+    del step, At, plan, H, peer, comm, dOut, W, U
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline_of(res, stages_key, dom, peak, peak_src, traffic=None):
+    st = res[stages_key] if stages_key == "stages" else res["dense"]["stages"]
+    algb = res["alg"] if stages_key == "stages" else res["dense"]["alg"]
+    achieved = algb[dom] / (st[dom]["ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "spmm_rows (forward SpMM, all slices in one launch)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algb[dom]}
+
+
+def slim(res, peak):
+    """the part of a workload's measurements that goes into the strong_scaling / same_config sub-objects"""
+    out = {k: res[k] for k in ("config", "scaling", "T_total", "ms_per_step", "value", "steps", "warmup",
+                               "slice_edges_per_step", "slice_edges_per_rank", "halo_mode", "backward_mode",
+                               "stages", "stages_ms_per_rank")}
+    out["layer_hbm_frac"] = res["layer_algorithmic_bytes"] / (res["ms_per_step"] * 1e-3) / 1e9 / peak
+    if "dense" in res:
+        out["dense"] = {k: res["dense"][k] for k in ("ms_per_step", "value", "stages", "stages_ms_per_rank")}
+    return out
+
+
+def run_ours(args):
+    from tmgcn_b200 import _lib
+    ctx = Ctx(args)
+    _lib.load(build_if_missing=False)
+    world, rank = ctx.world, ctx.rank
+    peak, peak_src = peaks()
+    extras = not args.no_extras and args.preset == "c5shard"
+
+    parity = None
+    if world > 1 and not args.no_extras:
+        from tmgcn_b200 import selfcheck
+        try:
+            parity = selfcheck.multi_gpu_parity(rank, world, ctx.dev, try_peer=(ctx.halo_mode == "peer"))
+        except Exception as ex:  # the check must never hide a crash: report it as a failed check
+            parity = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    wl = resolve_workload(args)
+    res = run_workload(wl, ctx, args.steps, args.warmup, full=True)
+
+    strong, same_cfg = {}, None
+    if extras:
+        k_x = max(3, min(args.steps, 10))
+        for name in ("c5cut", "c4"):
+            try:
+                r = run_workload(resolve_workload(args, name, cli=False), ctx, k_x, 3, full=False)
+                strong[name] = slim(r, peak)
+            except Exception as ex:
+                strong[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        if world == 1:
+            try:
+                wl1 = resolve_workload(args, "c1f128", cli=False)
+                r = run_workload(wl1, ctx, k_x, 3, full=False)
+                same_cfg = {"gpu": slim(r, peak)}
+                if not args.no_cpu_baseline:
+                    cb = cpu_run(wl1, wl1["nodes"], wl1["total_slices"], wl1["pairs"], 1, 0, "the whole workload")
+                    same_cfg["cpu"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                    same_cfg["ratio"] = r["value"] / cb["value"]
+                    same_cfg["ratio_dense_backward"] = r["dense"]["value"] / cb["value"] if "dense" in r else None
+                    same_cfg["note"] = ("both arms ran this whole workload on the same seeded graph (generated on the "
+                                        "host); the CPU arm is one timed step without warm-up")
+            except Exception as ex:
+                same_cfg = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
-        peak, peak_src = peaks()
-        l2 = torch.cuda.get_device_properties(dev).L2_cache_size
-        alg = step.algorithmic_bytes(l2)
-        stages = {k: sum(v) / len(v) for k, v in stage_times.items()}
-        for k in ("stencil_fwd", "spmm_fwd", "gemm_fwd", "readout_fwd", "readout_bwd", "gemm_bwd", "spmm_bwd",
-                  "stencil_bwd"):
-            stages.setdefault(k, float("nan"))
         dom = "spmm_fwd"
-        achieved = alg[dom] / (stages[dom] * 1e-3) / 1e9
-        per_stage = {k: {"ms": round(stages[k], 3),
-                         "GB/s": round(alg[k] / (stages[k] * 1e-3) / 1e9, 1) if k in alg else None}
-                     for k in stages}
-        sec = ms * 1e-3 / args.steps
-        sec_e2e = ms_e2e * 1e-3 / args.steps
-        layer_bytes = sum(alg.values())
         line = {
-            "metric": "TM-GCN layer fwd+bwd slice-edges/s", "value": slice_edges / sec, "unit": "slice-edges/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_name(args, T_local),
-            "slice_edges_per_step": slice_edges, "input_edges_per_step": nnz_in_total,
-            "clocks": clocks,
-            "e2e": {"value": slice_edges / sec_e2e, "unit": "slice-edges/s",
-                    "h2d_bytes_per_step": dOut_host.numel() * 4,
-                    "d2h_bytes_per_step": (out_host.numel() + dW_host.numel() + dU_host.numel()) * 4,
-                    "ms_per_step": sec_e2e * 1e3,
-                    "what": "LayerStep.forward+backward through the C ABI; per step dOut (E x C, the host-side loss "
-                            "gradient) comes from pinned host memory and logits + dW + dU go back to the host; "
-                            "H, A~ and the edge list stay device-resident as the reference's ctor caches them "
-                            "(ehf:195-198)"},
-            "gpu_launches": launches,
-            "halo": {"forward": halo_mode,
+            "metric": METRIC, "value": res["value"], "unit": "slice-edges/s", "n_gpus": world, "steps": res["steps"],
+            "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": res["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": res["config"],
+            "slice_edges_per_step": res["slice_edges_per_step"], "input_edges_per_step": res["input_edges_per_step"],
+            "slice_edges_per_rank": res["slice_edges_per_rank"],
+            "clocks": res["clocks"], "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"],
+            "halo": {"forward": res["halo_mode"],
                      "note": "peer = boundary stencil loads the predecessor's b-1 slices from its HBM over NVLink "
                              "(symmetric memory), fused into the kernel; nccl = send/recv on a side stream"},
-            "backward": {"mode": step.bwd_mode,
+            "backward": {"mode": res["backward_mode"],
                          "note": "lowrank = exact re-association of the backward through the rank-2C factor the "
-                                 "C-class readout hands back (linear layer, act=none); dense = general path",
-                         "dense_ms_per_step": None if ms_dense is None else ms_dense / args.steps,
-                         "dense_value": None if ms_dense is None else slice_edges / (ms_dense * 1e-3 / args.steps)},
-            "roofline": {"bound": "hbm", "kernel": "spmm_rows (forward SpMM, all slices in one launch)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args, T_local) if world == 1 else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg[dom]},
-            "layer_hbm_frac": layer_bytes / sec / 1e9 / peak,
-            "layer_algorithmic_bytes": layer_bytes,
-            "stages": per_stage,
-            "stages_ms_per_rank": stages_all,
-            "mtransform_sparse": {"seconds": t_tr, "transform_edges_per_s": slice_edges_local / t_tr,
-                                  "algorithmic_bytes": tr_bytes, "GB/s": tr_bytes / t_tr / 1e9,
-                                  "hbm_frac": tr_bytes / t_tr / 1e9 / peak,
-                                  "note": "stage (a), rank-0 shard: count pass + scan + fill pass, best of two warm runs, CUDA events "
-                                          "(includes the host read of the output size); bit-identical to the cold run"},
+                                 "C-class readout hands back (linear layer, act=none); dense = the general layer of "
+                                 "SURVEY 8(d) (any activation), timed in the same run: see `dense`",
+                         "dense_ms_per_step": res["dense"]["ms_per_step"] if "dense" in res else None,
+                         "dense_value": res["dense"]["value"] if "dense" in res else None},
+            "roofline": roofline_of(res, "stages", dom, peak, peak_src, measured_traffic(wl, res["T_own"], world)),
+            "layer_hbm_frac": res["layer_algorithmic_bytes"] / (res["ms_per_step"] * 1e-3) / 1e9 / peak,
+            "layer_algorithmic_bytes": res["layer_algorithmic_bytes"],
+            "stages": res["stages"], "stages_ms_per_rank": res["stages_ms_per_rank"],
         }
+        if "dense" in res:
+            d = res["dense"]
+            line["dense"] = {"what": "the same step with the general dense-gradient backward (what any activation "
+                                     "takes): readout bwd -> act' -> dP, dW -> SpMM^T -> stencil^T",
+                             "ms_per_step": d["ms_per_step"], "value": d["value"], "stages": d["stages"],
+                             "stages_ms_per_rank": d["stages_ms_per_rank"],
+                             "layer_hbm_frac": d["layer_algorithmic_bytes"] / (d["ms_per_step"] * 1e-3) / 1e9 / peak,
+                             "roofline": roofline_of(res, "dense", "spmm_bwd", peak, peak_src)}
+            line["dense"]["roofline"]["kernel"] = "spmm_rows on the transposed CSR (backward SpMM)"
+        if "mtransform_sparse" in res:
+            ms_ = res["mtransform_sparse"]
+            ms_["hbm_frac"] = ms_["GB/s"] / peak
+            line["mtransform_sparse"] = ms_
+        if parity is not None:
+            line["parity_multi_gpu"] = parity
+        if strong:
+            line["strong_scaling"] = strong
+        if same_cfg is not None:
+            line["same_config"] = same_cfg
+            line["extra"] = {"same_config_ratio": same_cfg.get("ratio")}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb = cpu_sample(args)
+                N, T, m, whole = cpu_sample_shape(args, wl)
+                cb = cpu_run(wl, N, T, m, 1, 0, "the whole workload" if whole else
+                             "bounded sample of the workload (same density, band and widths)")
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as ex:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "slice-edges/s", "cores": None, "kind": "port",
                                         "sample": f"failed: {ex}"}
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

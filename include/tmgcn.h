@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TMGCN_ABI_VERSION 1
+#define TMGCN_ABI_VERSION 2
 
 /* epilogue / nonlinearity selector (ref: ehf:284-289) */
 enum tmgcn_act { TMGCN_ACT_NONE = 0, TMGCN_ACT_RELU = 1, TMGCN_ACT_LEAKY = 2, TMGCN_ACT_SELU = 3 };
@@ -115,9 +115,11 @@ int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int h
 /* forward with the input in two pieces: the `halo` predecessor slices at x_halo, the own slices at x_own.
  * x_halo may point into a PEER GPU's memory (CUDA IPC / symmetric memory mapped over NVLink): the halo
  * exchange is then fused into the stencil -- the kernel loads the predecessor's slices straight from its
- * HBM, no staging copy and no halo region in the local tensor. */
+ * HBM, no staging copy and no halo region in the local tensor.  max_ctas > 0 runs it as a persistent grid
+ * of at most that many 128-thread CTAs: the peer-reading launch is NVLink-bound, and a full grid of
+ * stalled CTAs would take the registers the interior stencil / SpMM running beside it need (0 = full grid). */
 int tmgcn_mtransform_dense_fwd_split(const float *x_halo, const float *x_own, float *x_out, int T_out, int halo,
-                                     int64_t NF, const float *band_w, int b, void *stream);
+                                     int64_t NF, const float *band_w, int b, int max_ctas, void *stream);
 /* same, but only input slices s in [s_begin, s_end) of g_in are written (the others are left untouched):
  * lets a rank produce the `halo` slices it owes its predecessor first (and put them on the wire) and the
  * rest later, in place, without a staging copy. */

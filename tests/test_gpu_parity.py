@@ -18,7 +18,8 @@ TOL_GRAD = 1e-4
 @pytest.fixture(scope="module")
 def tg():
     import tmgcn_b200
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device (the product has no CPU fallback)")
     tmgcn_b200._lib.load(build_if_missing=False)   # the shipped .so must be there: no fallback
     return tmgcn_b200
 

@@ -17,7 +17,8 @@ TOL_OUT, TOL_GRAD = 1e-5, 1e-4
 @pytest.fixture(scope="module")
 def tg():
     import tmgcn_b200
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device (the product has no CPU fallback)")
     tmgcn_b200._lib.load(build_if_missing=False)
     return tmgcn_b200
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/tmgcn.h but not exported"
         assert s in _lib.PROTOTYPES, f"{s} has no ctypes prototype"
     assert sorted(_lib.PROTOTYPES) == syms
-    assert lib.tmgcn_abi_version() == 1
+    assert lib.tmgcn_abi_version() == 2
     assert isinstance(lib.tmgcn_last_error(), bytes)
     # size queries are host-only and safe without a GPU
     assert lib.tmgcn_scan_ws_bytes(10_000) >= 8
@@ -179,4 +179,4 @@ def test_header_is_plain_c(tmp_path):
     subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ltmgcn_b200",
                     "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.split() == ["1", "0"], (r.stdout, r.stderr)
+    assert r.returncode == 0 and r.stdout.split() == ["2", "0"], (r.stdout, r.stderr)

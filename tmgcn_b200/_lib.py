@@ -37,7 +37,7 @@ PROTOTYPES = {
     "tmgcn_mtransform_dense_bwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_solve_fwd": (_i, [_p, _p, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_solve_bwd": (_i, [_p, _p, _i, _l, _p, _i, _p]),
-    "tmgcn_mtransform_dense_fwd_split": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _p]),
+    "tmgcn_mtransform_dense_fwd_split": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _i, _p]),
     "tmgcn_mtransform_dense_bwd_range": (_i, [_p, _p, _i, _i, _l, _p, _i, _i, _i, _p]),
     "tmgcn_spmm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _l, _i, _i, _p]),
     "tmgcn_gemm_xw_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),
@@ -74,7 +74,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.tmgcn_abi_version() != 1:
+    if lib.tmgcn_abi_version() != 2:
         raise RuntimeError("libtmgcn_b200.so: ABI version mismatch")
     _lib = lib
     return lib

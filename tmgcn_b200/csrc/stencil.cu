@@ -71,14 +71,15 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
     constexpr int C = STENCIL_C, R = ring_size(B);
     extern __shared__ float sw[];
     load_weights<B>(sw, band_w, T_out, b);
-    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= n_vec) return;
+    const int T_in = halo + T_out;
+    // one column per thread; a capped grid (the peer-memory boundary launch) strides over the columns
+    for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < n_vec;
+         pos += (int64_t)gridDim.x * blockDim.x) {
     // forward: the first `halo` input slices come from src_halo (which may be a peer GPU's memory mapped
     // over NVLink: the halo exchange is then fused into this kernel), the rest from src
     const VT *in_halo = reinterpret_cast<const VT *>(src_halo) + pos;
     const VT *in = reinterpret_cast<const VT *>(src) + pos - (REVERSE ? 0 : (int64_t)halo * n_vec);
     VT *out = reinterpret_cast<VT *>(dst) + pos;
-    const int T_in = halo + T_out;
     VT ring[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) zero_v(ring[k]);
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
                 }
             }
         }
+    }
     }
 }
 
@@ -201,24 +203,29 @@ static int solve_entry(const float *z, float *y, int T, int64_t NF, const float 
 
 template <int B, int V, bool REVERSE>
 static int launch_stencil(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
-                          const float *band_w, int b, int s_begin, int s_end, cudaStream_t st) {
+                          const float *band_w, int b, int s_begin, int s_end, int max_ctas, cudaStream_t st) {
     const int64_t n_vec = NF / V;
     const size_t smem = (size_t)(T_out + 2 * B) * B * sizeof(float);
     TMGCN_REQUIRE(smem <= 200 * 1024, "mtransform_dense: T_out=%d too large for the weight table (b=%d)", T_out, b);
     auto kern = stencil_kernel<B, V, REVERSE>;
     if (smem > 48 * 1024) TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = 256;
-    kern<<<(unsigned)ceil_div(n_vec, threads), threads, smem, st>>>(src_halo, src, dst, T_out, halo, n_vec, band_w, b,
-                                                                    s_begin, s_end);
+    // max_ctas > 0: a small persistent grid of 128-thread CTAs (the boundary launch that reads a peer GPU's
+    // memory: it is NVLink-bound, and a full grid of stalled CTAs would hold the registers the concurrently
+    // running interior stencil / SpMM need)
+    const int threads = max_ctas > 0 ? 128 : 256;
+    int64_t grid = ceil_div(n_vec, threads);
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    kern<<<(unsigned)grid, threads, smem, st>>>(src_halo, src, dst, T_out, halo, n_vec, band_w, b, s_begin, s_end);
     return after_launch(REVERSE ? "stencil_bwd" : "stencil_fwd");
 }
 
 template <int V, bool REVERSE>
 static int dispatch_b(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
-                      const float *band_w, int b, int s_begin, int s_end, cudaStream_t st) {
+                      const float *band_w, int b, int s_begin, int s_end, int max_ctas, cudaStream_t st) {
 #define TMGCN_CASE(BB)                                                                                             \
     if (b <= BB)                                                                                                   \
-        return launch_stencil<BB, V, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
+        return launch_stencil<BB, V, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end,     \
+                                              max_ctas, st);
     TMGCN_CASE(1)
     TMGCN_CASE(2)
     TMGCN_CASE(4)
@@ -237,7 +244,7 @@ static int dispatch_b(const float *src_halo, const float *src, float *dst, int T
 
 template <bool REVERSE>
 static int stencil_entry(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
-                         const float *band_w, int b, int s_begin, int s_end, void *stream) {
+                         const float *band_w, int b, int s_begin, int s_end, void *stream, int max_ctas = 0) {
     TMGCN_REQUIRE(T_out >= 0 && NF >= 0 && halo >= 0, "mtransform_dense: negative size");
     TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform_dense: band width b=%d outside [1, 32]", b);
     TMGCN_REQUIRE(halo <= b - 1, "mtransform_dense: halo=%d exceeds b-1=%d", halo, b - 1);
@@ -246,8 +253,9 @@ static int stencil_entry(const float *src_halo, const float *src, float *dst, in
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec4 = (NF % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) &&
                       ((uintptr_t)src_halo % 16 == 0);
-    if (vec4) return dispatch_b<4, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
-    return dispatch_b<1, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, st);
+    if (vec4)
+        return dispatch_b<4, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, max_ctas, st);
+    return dispatch_b<1, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, max_ctas, st);
 }
 
 }  // namespace tmgcn
@@ -260,13 +268,17 @@ int tmgcn_mtransform_dense_fwd(const float *x_in, float *x_out, int T_out, int h
                                        0, halo + T_out, stream);
 }
 int tmgcn_mtransform_dense_fwd_split(const float *x_halo, const float *x_own, float *x_out, int T_out, int halo,
-                                     int64_t NF, const float *band_w, int b, void *stream) {
+                                     int64_t NF, const float *band_w, int b, int max_ctas, void *stream) {
     if (halo > 0 && !x_halo) {
         tmgcn::set_error("mtransform_dense_fwd_split: null halo pointer");
         return 1;
     }
+    if (max_ctas < 0) {
+        tmgcn::set_error("mtransform_dense_fwd_split: negative max_ctas");
+        return 1;
+    }
     return tmgcn::stencil_entry<false>(halo > 0 ? x_halo : x_own, x_own, x_out, T_out, halo, NF, band_w, b, 0,
-                                       halo + T_out, stream);
+                                       halo + T_out, stream, max_ctas);
 }
 int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                const float *band_w, int b, void *stream) {

@@ -37,6 +37,7 @@ Same gradients to rounding (parity-tested against the CPU restatement of the ref
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -47,8 +48,13 @@ from .ops import ACT, Band, EdgePlan, SliceCSR, _p, _stream
 
 class LayerStep:
     def __init__(self, At: SliceCSR, band: Band, plan: EdgePlan, F_in: int, F_out: int, C: int, act=None,
-                 t0: int = 0, t1: Optional[int] = None, halo: int = 0, bwd_mode: str = "auto"):
+                 t0: int = 0, t1: Optional[int] = None, halo: int = 0, bwd_mode: str = "auto",
+                 boundary_ctas: Optional[int] = None):
         self.lib = _lib.load()
+        if boundary_ctas is None:     # persistent grid of the peer-reading boundary stencil (0 = full grid)
+            boundary_ctas = int(os.environ.get("TMGCN_BOUNDARY_CTAS", 2 * torch.cuda.get_device_properties(
+                At.rowptr.device).multi_processor_count))
+        self.boundary_ctas = boundary_ctas
         self.At, self.AtT = At, At.transpose()
         self.band, self.plan = band, plan
         self.t0, self.t1, self.halo = t0, (band.T if t1 is None else t1), halo
@@ -127,7 +133,8 @@ class LayerStep:
 
             def boundary():     # outputs [0, hb): halo slices from the predecessor's HBM, the rest from ours
                 _lib.check(lib.tmgcn_mtransform_dense_fwd_split(_p(peer.tail()), _p(H), _p(Ht), hb, self.halo, NF,
-                                                                _p(self.w_f32), self.band.b, _stream()))
+                                                                _p(self.w_f32), self.band.b, self.boundary_ctas,
+                                                                _stream()))
             peer.run_boundary(boundary)
         elif comm is not None:
             self._mark("halo_fwd_start")
@@ -152,6 +159,9 @@ class LayerStep:
         self._mark("readout_fwd")
         _lib.check(lib.tmgcn_edge_readout_fwd(_p(Y), _p(self.plan.src), _p(self.plan.dst), _p(U), _p(self.out),
                                               self.plan.E, self.F_out, self.C, st))
+        if peer is not None:
+            # whatever rewrites H after this call is ordered after every rank's NVLink reads of this step
+            peer.wait_reads_done()
         self._mark("end")
         return self.out
 

@@ -89,10 +89,13 @@ class _Base(nn.Module):
         cache = self.__dict__.setdefault("_csr_cache", {})
         key = id(A)
         hit = cache.get(key)
-        if hit is not None and hit[0] is A:
-            return hit[1]
+        # a hit needs the same list object holding the same slice objects (a list mutated in place is rebuilt)
+        if hit is not None and hit[0] is A and len(hit[1]) == len(A) and all(x is y for x, y in zip(hit[1], A)):
+            return hit[2]
         csr = SliceCSR.from_slice_list(A, N)
-        cache[key] = (A, csr)
+        while len(cache) >= 4:                      # train / val / test lists + one spare: bounded, oldest first
+            cache.pop(next(iter(cache)))
+        cache[key] = (A, list(A), csr)
         return csr
 
     @staticmethod
@@ -130,7 +133,7 @@ class EmbeddingGCN(_Base):
             self.W = self._param(self.T, self.F[0], self.F[1])
         self.U = self._param(2 * self.F[1], self.F[2])
         self.AtXt = self.compute_AtXt(At, X)                  # ref: ehf:195
-        self.edge_plan = EdgePlan(edges, self.N)              # ref: ehf:196-198
+        self.edge_plan = EdgePlan(edges, self.N, T=self.T)              # ref: ehf:196-198
 
     def compute_AtXt(self, At, X):
         """(T, N, F) fp32 = facewise At[k] @ (M x_3 X)[k] (ref: ehf:203-208)."""
@@ -141,7 +144,7 @@ class EmbeddingGCN(_Base):
     def forward(self, At=None, X=None, edges=None):
         if self._fresh(At, X, edges):
             AtXt = self.compute_AtXt(At, X)
-            plan = EdgePlan(edges, self.N)
+            plan = EdgePlan(edges, self.N, T=int(X.shape[0]))
         else:
             AtXt, plan = self.AtXt, self.edge_plan
         if self.use_Minv or not self.condensed_W:             # general path (ehf:222-232)
@@ -179,7 +182,7 @@ class EmbeddingGCN2(_Base):
         self.nonlin2 = _act_name(nonlin2)
         self.At_csr = self._csr(At, self.N)
         self.AtXt = self.compute_AtXt(At, X)
-        self.edge_plan = EdgePlan(edges, self.N)
+        self.edge_plan = EdgePlan(edges, self.N, T=self.T)
 
     def compute_AX(self, A, X):
         """facewise A[k] @ X[k] (ref: ehf:301-305); differentiable w.r.t. X."""
@@ -197,7 +200,7 @@ class EmbeddingGCN2(_Base):
     def forward(self, At=None, X=None, edges=None):
         if self._fresh(At, X, edges):
             AtXt = self.compute_AtXt(At, X)
-            plan = EdgePlan(edges, self.N)
+            plan = EdgePlan(edges, self.N, T=int(X.shape[0]))
         else:
             AtXt, plan = self.AtXt, self.edge_plan
         if self.use_Minv or not self.condensed_W:             # general path, ehf:330-349 branch by branch
@@ -270,7 +273,7 @@ class EmbeddingKWGCN(_Base):
         self.U = self._param(self.F[-2] * 2, self.F[-1])
         self.nonlin2 = _act_name(nonlin2)
         self.A_csr = self._csr(A, self.N)
-        self.edge_plan = EdgePlan(edges, self.N)
+        self.edge_plan = EdgePlan(edges, self.N, T=self.T)
         self.AX = self.compute_AX(A, X)
 
     def compute_AX(self, A, X):
@@ -283,7 +286,7 @@ class EmbeddingKWGCN(_Base):
     def forward(self, A=None, X=None, edges=None):
         if self._fresh(A, X, edges):
             AX = self.compute_AX(A, X)
-            plan = EdgePlan(edges, self.N)
+            plan = EdgePlan(edges, self.N, T=int(X.shape[0]))
         else:
             AX, plan = self.AX, self.edge_plan
         if self.no_layers == 2:                               # ref: ehf:486-487, 491-495

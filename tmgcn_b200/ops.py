@@ -27,15 +27,27 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+def _p(t: Optional[torch.Tensor], dtype: Optional[torch.dtype] = None) -> C.c_void_p:
+    """raw device pointer of a contiguous CUDA tensor; `dtype` = what the kernel will read it as (the
+    library takes untyped pointers, so a tensor of another dtype would be silently reinterpreted)."""
     if t is None:
         return C.c_void_p(0)
-    assert t.is_cuda and t.is_contiguous(), "tmgcn: expected a contiguous CUDA tensor"
+    if not (t.is_cuda and t.is_contiguous()):
+        raise ValueError("tmgcn: expected a contiguous CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"tmgcn: expected a {dtype} tensor, got {t.dtype}")
     return C.c_void_p(t.data_ptr())
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
+    """contiguous fp32 tensor on the current CUDA device (no copy when it already is one): every public
+    entry point funnels caller tensors through this, e.g. the reference's fp64 X (ehf:204 feeds .double())"""
+    if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+        return t
     return t.to(device=_dev(), dtype=torch.float32).contiguous()
+
+
+_F, _L, _I = torch.float32, torch.int64, torch.int32
 
 
 def _ws(nbytes: int) -> torch.Tensor:
@@ -78,8 +90,21 @@ class SliceCSR:
         (replaces the per-slice masking of ref: ehf:561-572)."""
         lib = _lib.load()
         dev = _dev()
-        idx = idx.to(dev)
+        idx = idx.to(device=dev, dtype=torch.int64)
+        if idx.dim() != 2 or idx.shape[0] != 3 or val.numel() != idx.shape[1]:
+            raise ValueError("from_coo: idx must be (3, nnz) with one value per column")
         flat = (idx[0] * N + idx[1]).contiguous()
+        if flat.numel():
+            # validated once here: the row-pointer kernel writes rowptr[r] for every r up to rows[k], so an
+            # out-of-range or unsorted entry would be an out-of-bounds device write / uninitialised rowptr
+            lo = torch.stack([idx[0].min(), idx[1].min(), idx[2].min()])
+            hi = torch.stack([idx[0].max() - T, idx[1].max() - N, idx[2].max() - N])
+            if bool((lo < 0).any()) or bool((hi >= 0).any()):
+                raise ValueError(f"from_coo: an index is outside the {T} x {N} x {N} tensor")
+            key = flat * N + idx[2]
+            if bool((key[1:] <= key[:-1]).any()):
+                raise ValueError("from_coo: entries must be coalesced (strictly ascending (t, i, j) order)")
+            del key
         col = idx[2].to(torch.int32).contiguous()
         val = val.to(device=dev, dtype=dtype).contiguous()
         rowptr = torch.empty(T * N + 1, dtype=torch.int64, device=dev)
@@ -205,11 +230,12 @@ def stencil_fwd(x: torch.Tensor, band: Band, t0: int = 0, t1: Optional[int] = No
     lib = _lib.load()
     t1 = band.T if t1 is None else t1
     T_out = t1 - t0
+    x = _f32(x)
     assert x.shape[0] == T_out + halo, "x must hold halo + T_out slices"
     NF = x[0].numel() if x.shape[0] else 0
     out = torch.empty((T_out,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
     w = band.device_weights(t0, t1, torch.float32)
-    _lib.check(lib.tmgcn_mtransform_dense_fwd(_p(x), _p(out), T_out, halo, NF, _p(w), band.b, _stream()))
+    _lib.check(lib.tmgcn_mtransform_dense_fwd(_p(x, _F), _p(out, _F), T_out, halo, NF, _p(w, _F), band.b, _stream()))
     return out
 
 
@@ -217,36 +243,41 @@ def stencil_bwd(g: torch.Tensor, band: Band, t0: int = 0, t1: Optional[int] = No
     lib = _lib.load()
     t1 = band.T if t1 is None else t1
     T_out = t1 - t0
+    g = _f32(g)
     assert g.shape[0] == T_out
     NF = g[0].numel() if g.shape[0] else 0
     out = torch.empty((T_out + halo,) + tuple(g.shape[1:]), dtype=torch.float32, device=g.device)
     w = band.device_weights(t0, t1, torch.float32)
-    _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(g), _p(out), T_out, halo, NF, _p(w), band.b, _stream()))
+    _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(g, _F), _p(out, _F), T_out, halo, NF, _p(w, _F), band.b, _stream()))
     return out
 
 
 def spmm_raw(csr: SliceCSR, x: torch.Tensor, act: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
+    x = _f32(x)
     assert x.dim() == 3 and x.shape[0] == csr.T and x.shape[1] == csr.N, "x must be (T, N, F)"
     if csr.val.dtype != torch.float32:
         raise TypeError("spmm: fp32 CSR values only")
     y = torch.empty_like(x) if out is None else out
-    _lib.check(lib.tmgcn_spmm_fwd(_p(csr.rowptr), _p(csr.col), _p(csr.val), _p(x), _p(y), csr.T, csr.N,
-                                  x.shape[2], act, _stream()))
+    _lib.check(lib.tmgcn_spmm_fwd(_p(csr.rowptr, _L), _p(csr.col, _I), _p(csr.val, _F), _p(x, _F), _p(y, _F), csr.T,
+                                  csr.N, x.shape[2], act, _stream()))
     return y
 
 
 def gemm_fwd_raw(p: torch.Tensor, w: torch.Tensor, act: int = 0) -> torch.Tensor:
     lib = _lib.load()
+    p, w = _f32(p), _f32(w)
     K, Nf = w.shape
     R = p.numel() // K
     y = torch.empty(tuple(p.shape[:-1]) + (Nf,), dtype=torch.float32, device=p.device)
-    _lib.check(lib.tmgcn_gemm_xw_fwd(_p(p), _p(w), _p(y), R, K, Nf, act, _stream()))
+    _lib.check(lib.tmgcn_gemm_xw_fwd(_p(p, _F), _p(w, _F), _p(y, _F), R, K, Nf, act, _stream()))
     return y
 
 
 def gemm_bwd_raw(p, w, y, dy, act: int, need_dp: bool = True, need_dw: bool = True):
     lib = _lib.load()
+    p, w, dy = _f32(p), _f32(w), _f32(dy)
+    y = None if y is None else _f32(y)
     K, Nf = w.shape
     R = dy.numel() // Nf
     dp = torch.empty(tuple(dy.shape[:-1]) + (K,), dtype=torch.float32, device=dy.device) if need_dp else None
@@ -261,11 +292,25 @@ class EdgePlan:
     """Flat endpoint ids (ref: ehf:196-198) plus, lazily, the incidence list that
     makes the backward scatter-add deterministic."""
 
-    def __init__(self, edges: torch.Tensor, N: int, t_offset: int = 0):
+    def __init__(self, edges: torch.Tensor, N: int, t_offset: int = 0, T: Optional[int] = None):
+        """edges (3, E): time, src, dst (ref: ehf:169-170); `t_offset` is subtracted from the times (the first
+        slice a shard owns); with `T` the times are range-checked too.  The reference raises IndexError on an
+        out-of-range edge; here it would be an out-of-bounds device access, so the range is checked once."""
         lib = _lib.load()
         edges = edges.to(device=_dev(), dtype=torch.int64).contiguous()
-        assert edges.dim() == 2 and edges.shape[0] == 3, "edges must be (3, E): time, src, dst"
+        if edges.dim() != 2 or edges.shape[0] != 3:
+            raise ValueError("edges must be (3, E): time, src, dst")
         self.E = int(edges.shape[1])
+        self.n_rows_checked = None
+        if self.E:
+            lo = edges.min(dim=1).values
+            hi = edges.max(dim=1).values
+            bad = bool((lo[1:] < 0).any()) or bool((hi[1:] >= N).any()) or int(lo[0]) - t_offset < 0
+            if T is not None:
+                bad = bad or int(hi[0]) - t_offset >= T
+                self.n_rows_checked = T * N
+            if bad:
+                raise ValueError(f"edge index out of range (N = {N}, T = {T}, first slice = {t_offset})")
         self.src = torch.empty(self.E, dtype=torch.int64, device=edges.device)
         self.dst = torch.empty(self.E, dtype=torch.int64, device=edges.device)
         _lib.check(lib.tmgcn_flat_edge_ids(_p(edges), self.E, N, t_offset, _p(self.src), _p(self.dst), _stream()))
@@ -276,6 +321,8 @@ class EdgePlan:
         if self._inc is None or self._inc[0] != n_rows:
             lib = _lib.load()
             E, dev = self.E, self.src.device
+            if E and self.n_rows_checked != n_rows and int(torch.maximum(self.src.max(), self.dst.max())) >= n_rows:
+                raise ValueError(f"an edge endpoint lies outside the {n_rows} rows of the embedding tensor")
             keys = torch.cat([self.src, self.dst])
             ar = torch.arange(E, device=dev, dtype=torch.int64)
             code = torch.cat([2 * ar, 2 * ar + 1])
@@ -292,6 +339,7 @@ class EdgePlan:
 
 def readout_fwd_raw(y2d: torch.Tensor, plan: EdgePlan, u: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
+    y2d, u = _f32(y2d), _f32(u)
     F, Cc = y2d.shape[1], u.shape[1]
     assert u.shape[0] == 2 * F
     out = torch.empty(plan.E, Cc, dtype=torch.float32, device=y2d.device)
@@ -302,6 +350,7 @@ def readout_fwd_raw(y2d: torch.Tensor, plan: EdgePlan, u: torch.Tensor) -> torch
 
 def readout_bwd_raw(y2d, plan: EdgePlan, u, dout, need_dy=True, need_du=True):
     lib = _lib.load()
+    y2d, u, dout = _f32(y2d), _f32(u), _f32(dout)
     F, Cc = y2d.shape[1], u.shape[1]
     inc_ptr, perm = plan.incidence(y2d.shape[0])
     dy = torch.empty_like(y2d) if need_dy else None
@@ -320,12 +369,12 @@ class _Stencil(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, band, t0, t1, halo):
         ctx.args = (band, t0, t1, halo)
-        return stencil_fwd(x.contiguous(), band, t0, t1, halo)
+        return stencil_fwd(_f32(x), band, t0, t1, halo)
 
     @staticmethod
     def backward(ctx, g):
         band, t0, t1, halo = ctx.args
-        return stencil_bwd(g.contiguous(), band, t0, t1, halo), None, None, None, None
+        return stencil_bwd(_f32(g), band, t0, t1, halo), None, None, None, None
 
 
 class _Solve(torch.autograd.Function):
@@ -334,7 +383,7 @@ class _Solve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, band):
         lib = _lib.load()
-        z = z.contiguous()
+        z = _f32(z)
         y = torch.empty_like(z)
         w = band.device_weights(0, band.T, torch.float32)
         assert z.shape[0] == band.T
@@ -346,7 +395,7 @@ class _Solve(torch.autograd.Function):
     def backward(ctx, g):
         lib = _lib.load()
         band = ctx.band
-        g = g.contiguous()
+        g = _f32(g)
         gz = torch.empty_like(g)
         w = band.device_weights(0, band.T, torch.float32)
         _lib.check(lib.tmgcn_mtransform_dense_solve_bwd(_p(g), _p(gz), band.T, g[0].numel(), _p(w), band.b, _stream()))
@@ -356,7 +405,7 @@ class _Solve(torch.autograd.Function):
 class _SpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, csr, act):
-        y = spmm_raw(csr, x.contiguous(), act)
+        y = spmm_raw(csr, _f32(x), act)
         ctx.csr, ctx.act = csr, act
         if act:
             ctx.save_for_backward(y)
@@ -365,7 +414,7 @@ class _SpMM(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
-        g = g.contiguous()
+        g = _f32(g)
         if ctx.act:
             (y,) = ctx.saved_tensors
             ge = torch.empty_like(g)
@@ -377,7 +426,7 @@ class _SpMM(torch.autograd.Function):
 class _Gemm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p, w, act):
-        p, w = p.contiguous(), w.contiguous()
+        p, w = _f32(p), _f32(w)
         y = gemm_fwd_raw(p, w, act)
         ctx.act = act
         ctx.save_for_backward(p, w, y if act else None)
@@ -386,7 +435,7 @@ class _Gemm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         p, w, y = ctx.saved_tensors
-        g = g.contiguous()
+        g = _f32(g)
         act = ctx.act
         if act:   # dY <- dY * act'(Y) once, so dP can take the tensor-core path
             lib = _lib.load()
@@ -400,8 +449,8 @@ class _Gemm(torch.autograd.Function):
 class _Readout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, u, plan):
-        y2d = y.contiguous().reshape(-1, y.shape[-1])
-        u = u.contiguous()
+        y2d = _f32(y).reshape(-1, y.shape[-1])
+        u = _f32(u)
         ctx.plan, ctx.shape = plan, y.shape
         ctx.save_for_backward(y2d, u)
         return readout_fwd_raw(y2d, plan, u)
@@ -409,7 +458,7 @@ class _Readout(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         y2d, u = ctx.saved_tensors
-        dy, du = readout_bwd_raw(y2d, ctx.plan, u, g.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        dy, du = readout_bwd_raw(y2d, ctx.plan, u, _f32(g), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return (dy.reshape(ctx.shape) if dy is not None else None), du, None
 
 
@@ -418,7 +467,7 @@ class _Gather(torch.autograd.Function):
     def forward(ctx, y, plan):
         lib = _lib.load()
         F = y.shape[-1]
-        y2d = y.contiguous().reshape(-1, F)
+        y2d = _f32(y).reshape(-1, F)
         z = torch.empty(plan.E, 2 * F, dtype=torch.float32, device=y.device)
         _lib.check(lib.tmgcn_edge_gather_fwd(_p(y2d), _p(plan.src), _p(plan.dst), _p(z), plan.E, F, _stream()))
         ctx.plan, ctx.shape = plan, y.shape
@@ -433,7 +482,7 @@ class _Gather(torch.autograd.Function):
             n_rows *= s
         inc_ptr, perm = ctx.plan.incidence(n_rows)
         dy = torch.empty(n_rows, F, dtype=torch.float32, device=g.device)
-        _lib.check(lib.tmgcn_edge_gather_bwd(_p(g.contiguous()), _p(inc_ptr), _p(perm), _p(dy), n_rows, F, _stream()))
+        _lib.check(lib.tmgcn_edge_gather_bwd(_p(_f32(g), _F), _p(inc_ptr), _p(perm), _p(dy), n_rows, F, _stream()))
         return dy.reshape(ctx.shape), None
 
 
@@ -441,7 +490,7 @@ class _Act(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, act):
         lib = _lib.load()
-        x = x.contiguous()
+        x = _f32(x)
         y = torch.empty_like(x)
         _lib.check(lib.tmgcn_act_fwd(_p(x), _p(y), x.numel(), act, _stream()))
         ctx.act = act
@@ -452,7 +501,7 @@ class _Act(torch.autograd.Function):
     def backward(ctx, g):
         lib = _lib.load()
         (y,) = ctx.saved_tensors
-        g = g.contiguous()
+        g = _f32(g)
         dx = torch.empty_like(g)
         _lib.check(lib.tmgcn_act_bwd(_p(y), _p(g), _p(dx), g.numel(), ctx.act, _stream()))
         return dx, None
@@ -465,13 +514,14 @@ def class_sums_raw(dout: torch.Tensor, plan: EdgePlan, n_rows: int) -> torch.Ten
     Cc = dout.shape[1]
     inc_ptr, perm = plan.incidence(n_rows)
     S = torch.empty(n_rows, 2 * Cc, dtype=torch.float32, device=dout.device)
-    _lib.check(lib.tmgcn_edge_class_sums(_p(dout.contiguous()), _p(inc_ptr), _p(perm), _p(S), n_rows, Cc, _stream()))
+    _lib.check(lib.tmgcn_edge_class_sums(_p(_f32(dout), _F), _p(inc_ptr), _p(perm), _p(S), n_rows, Cc, _stream()))
     return S
 
 
 def factor_reduce_raw(x2d: torch.Tensor, S: torch.Tensor, Cc: int) -> torch.Tensor:
     """G[(h, f), c] = sum_rows x[row, f] * S[row, h, c]  -> (2F, C)."""
     lib = _lib.load()
+    x2d, S = _f32(x2d), _f32(S)
     F = x2d.shape[1]
     G = torch.empty(2 * F, Cc, dtype=torch.float32, device=x2d.device)
     ws = _ws(lib.tmgcn_edge_factor_ws_bytes(F, Cc))
@@ -482,6 +532,7 @@ def factor_reduce_raw(x2d: torch.Tensor, S: torch.Tensor, Cc: int) -> torch.Tens
 def factor_expand_raw(S: torch.Tensor, Vu: torch.Tensor, F: int, Cc: int) -> torch.Tensor:
     """out[row, f] = sum_{h,c} S[row, h, c] * Vu[hF + f, c]  -> (n_rows, F)."""
     lib = _lib.load()
+    S, Vu = _f32(S), _f32(Vu)
     out = torch.empty(S.shape[0], F, dtype=torch.float32, device=S.device)
     _lib.check(lib.tmgcn_edge_factor_apply(None, _p(Vu), _p(S), _p(out), None, S.shape[0], F, Cc, None, _stream()))
     return out
@@ -510,7 +561,7 @@ class _PropagateLinearReadout(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, H, W, U, csr, band, plan):
-        H, W, U = H.contiguous(), W.contiguous(), U.contiguous()
+        H, W, U = _f32(H), _f32(W), _f32(U)
         Ht = stencil_fwd(H, band) if band is not None else H
         P = spmm_raw(csr, Ht) if csr is not None else Ht
         Y = gemm_fwd_raw(P, W)
@@ -522,6 +573,7 @@ class _PropagateLinearReadout(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         P, W, U = ctx.saved_tensors
+        g = _f32(g)
         Fi, Cc = W.shape[0], U.shape[1]
         n_rows = P.numel() // Fi
         S = class_sums_raw(g, ctx.plan, n_rows)

@@ -27,6 +27,46 @@ def shard_bounds(T: int, world: int, rank: int):
     return t0, t0 + base + (1 if rank < rem else 0)
 
 
+def balanced_bounds(weights, world: int):
+    """Contiguous blocks [(t0, t1)] * world over len(weights) slices whose summed weights are as even as
+    the slice granularity allows (greedy on the prefix sums: block r ends where the running weight is
+    closest to (r + 1) / world of the total).  Used to balance nnz(A~_t): the first b-1 windows of the
+    tensor are truncated, so equal slice counts leave rank 0 with less work."""
+    w = [float(x) for x in weights]
+    T = len(w)
+    if world < 1 or T < world:
+        raise ValueError(f"cannot split {T} slices over {world} ranks")
+    pre = [0.0]
+    for x in w:
+        pre.append(pre[-1] + x)
+    cuts = [0]
+    for r in range(1, world):
+        target = pre[-1] * r / world
+        lo, hi = cuts[-1] + 1, T - (world - r)          # leave at least one slice per remaining rank
+        best = min(range(lo, hi + 1), key=lambda t: (abs(pre[t] - target), t))
+        cuts.append(best)
+    cuts.append(T)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def slice_weight_estimate(T: int, b: int, N: int, m: int, rho: float):
+    """Expected nnz(A~_t) of the synthetic graphs (tmgcn_b200.synth): the diagonal plus 2m stored pairs, plus the
+    (1 - rho) share of each of the window's older slices that is no longer alive."""
+    return [N + 2.0 * m * (1.0 + (min(t + 1, b) - 1) * (1.0 - rho)) for t in range(T)]
+
+
+def assert_single_hop(T_own: int, h: int, world: int, device=None):
+    """Every rank's block must hold at least h = b-1 slices: a halo then comes from the predecessor alone and
+    the send / receive sizes of neighbouring ranks agree (ranks with fewer slices would need a multi-hop halo,
+    which is not implemented).  Collective: raises on every rank if any rank fails."""
+    if world <= 1:
+        return
+    t = torch.tensor([int(T_own)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) < h:
+        raise ValueError(f"time sharding needs at least b-1 = {h} slices per rank (smallest block: {int(t.item())})")
+
+
 def _chain(send: Optional[torch.Tensor], dst: int, recv: Optional[torch.Tensor], src: int):
     ops = []
     if send is not None:
@@ -42,8 +82,9 @@ def exchange_sparse_halo(A_own: SliceCSR, halo_out: int, rank: int, world: int) 
     """Return [last `halo_out` slices of rank-1's block | own slices] as one CSR-of-slices
     (rank 0: own slices unchanged).  Done once per dataset, before the sparse M-transform."""
     T, N = A_own.T, A_own.N
-    h = min(halo_out, T)
     dev = A_own.rowptr.device
+    assert_single_hop(T, halo_out, world, dev)
+    h = halo_out
     send_meta = recv_meta = None
     if rank < world - 1:
         r0 = (T - h) * N
@@ -74,8 +115,10 @@ def exchange_sparse_halo(A_own: SliceCSR, halo_out: int, rank: int, world: int) 
 class DenseHalo:
     """Per-step halo exchange of the dense layer input / its gradient."""
 
-    def __init__(self, NF: int, h: int, rank: int, world: int):
+    def __init__(self, NF: int, h: int, rank: int, world: int, T_own: Optional[int] = None, device=None):
         self.NF, self.h, self.rank, self.world = NF, h, rank, world
+        if T_own is not None:
+            assert_single_hop(T_own, h, world, device)
 
     def forward(self, H: torch.Tensor, T_own: int, halo: int):
         """H = [halo | T_own] slices.  Fill H[:halo] from the predecessor's last slices."""
@@ -109,8 +152,10 @@ class ShardComm:
               rank+1 owes us; the caller waits on `bwd_recv` and adds it.
     """
 
-    def __init__(self, h: int, rank: int, world: int, device):
+    def __init__(self, h: int, rank: int, world: int, device, T_own: Optional[int] = None):
         self.h, self.rank, self.world = h, rank, world
+        if T_own is not None:
+            assert_single_hop(T_own, h, world, device)
         self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.fwd_done = torch.cuda.Event()
         self.bwd_sent = torch.cuda.Event()
@@ -159,26 +204,57 @@ class PeerHalo:
 
     Every rank keeps its layer input H (T_own, N, F) in symmetric memory; rank r maps rank r-1's block and
     the boundary stencil kernel (`tmgcn_mtransform_dense_fwd_split`) loads the predecessor's last b-1 slices
-    straight from its HBM: no NCCL copy, no staging, no halo region in the local tensor.  Two stream-ordered
-    cross-rank barriers per step fence the reads: "every H is ready" before, "all reads are done" after
-    (the owner waits on `reads_done` before it overwrites H)."""
+    straight from its HBM: no NCCL copy, no staging, no halo region in the local tensor.  Blocks may differ
+    in length (nnz-balanced shards): the block lengths are all-gathered at construction and the tail is
+    indexed from the predecessor's real length.  Two stream-ordered cross-rank barriers per step fence the
+    reads: "every H is ready" before, "all reads are done" after; `LayerStep.forward` makes the caller's
+    stream wait on `reads_done` before it returns, so whatever rewrites H next is ordered after the
+    successor's NVLink reads.
 
-    def __init__(self, T_own: int, N: int, F: int, h: int, rank: int, world: int, device, group=None):
+    `storage` = (buffer, handle) of an existing symmetric allocation of at least T_own*N*F floats lets
+    several workloads share one allocation (symmetric memory is not returned to the caching allocator)."""
+
+    def __init__(self, T_own: int, N: int, F: int, h: int, rank: int, world: int, device, group=None,
+                 storage=None):
         import torch.distributed._symmetric_memory as symm_mem
-        self.T, self.N, self.F, self.h, self.rank, self.world = T_own, N, F, min(h, T_own), rank, world
-        self.buf = symm_mem.empty(T_own * N * F, dtype=torch.float32, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, (group or dist.group.WORLD).group_name)
-        self.H = self.buf.view(T_own, N, F)
-        self.prev = self.hdl.get_buffer(rank - 1, (T_own, N, F), torch.float32) if rank > 0 else None
+        self.T, self.N, self.F, self.rank, self.world = T_own, N, F, rank, world
+        lens = torch.zeros(world, dtype=torch.int64, device=device)
+        lens[rank] = T_own
+        dist.all_reduce(lens, group=group)
+        self.T_all = [int(x) for x in lens.tolist()]
+        if min(self.T_all) < h:
+            raise ValueError(f"PeerHalo needs at least b-1 = {h} slices per rank (blocks: {self.T_all})")
+        self.h = h
+        n_max = max(self.T_all) * N * F
+        if storage is None:
+            buf = symm_mem.empty(n_max, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, (group or dist.group.WORLD).group_name)
+        else:
+            buf, hdl = storage
+            if buf.numel() < n_max:
+                raise ValueError("PeerHalo: the shared symmetric buffer is too small for this workload")
+        self.buf, self.hdl = buf, hdl
+        self.H = buf[: T_own * N * F].view(T_own, N, F)
+        self.prev = None
+        if rank > 0:
+            Tp = self.T_all[rank - 1]
+            self.prev = hdl.get_buffer(rank - 1, (Tp, N, F), torch.float32)
         # high priority: the boundary kernel must not queue behind the main stream's persistent SpMM grid
         self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.boundary_done = torch.cuda.Event()
         self.reads_done = torch.cuda.Event()
         self._ready = torch.cuda.Event()
 
+    @staticmethod
+    def allocate(numel: int, device, group=None):
+        """one symmetric allocation (buffer, handle) to be shared by several PeerHalo objects"""
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(int(numel), dtype=torch.float32, device=device)
+        return buf, symm_mem.rendezvous(buf, (group or dist.group.WORLD).group_name)
+
     def tail(self) -> torch.Tensor:
         """the predecessor's last h slices -- a view of PEER memory"""
-        return self.prev[self.T - self.h:]
+        return self.prev[self.T_all[self.rank - 1] - self.h:]
 
     def run_boundary(self, fn):
         """fn() launches the peer-reading boundary stencil; runs on the side stream between the two barriers."""
@@ -192,6 +268,10 @@ class PeerHalo:
             self.boundary_done.record(self.stream)
             self.hdl.barrier(channel=1)          # every rank has finished reading its predecessor
             self.reads_done.record(self.stream)
+
+    def wait_reads_done(self):
+        """order the current stream after every rank's NVLink reads of this step (call before H is rewritten)"""
+        torch.cuda.current_stream().wait_event(self.reads_done)
 
 
 def allreduce_grads(grads: List[torch.Tensor]):
