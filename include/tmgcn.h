@@ -128,11 +128,19 @@ int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out,
 
 /* inverse transform  Y = inv(M) x_3 Z  (ref: Minv = inv(M), ehf:183-184; applied at ehf:223-224, 331-332,
  * 338-341): inv(M) of a banded M is dense, so it is applied as the banded substitution M x_3 Y = Z marching
- * through time (fp64 recurrence, fp32 in/out); _bwd solves with M^T (the adjoint).  Unsharded only (halo = 0). */
+ * through time (fp64 recurrence, fp32 in/out); _bwd solves with M^T (the adjoint).
+ * _part is the time-sharded, column-chunked form: it continues a recurrence started on another rank from `h`
+ * halo rows (forward: the predecessor's last h OUTPUT slices; transposed: the successor's first h output
+ * slices), works on n columns of rows that are `ld` floats apart (halo rows `ld_halo` apart), and -- transposed
+ * -- needs band_w to hold T + h rows (M[s+i, s] with s+i in the successor's block).  A caller pipelines the
+ * cross-rank scan over column chunks (tmgcn_b200/sharding.py: solve_pipelined). */
 int tmgcn_mtransform_dense_solve_fwd(const float *z, float *y, int T, int64_t NF, const float *band_w, int b,
                                      void *stream);
 int tmgcn_mtransform_dense_solve_bwd(const float *g_y, float *g_z, int T, int64_t NF, const float *band_w, int b,
                                      void *stream);
+int tmgcn_mtransform_dense_solve_part(const float *src, float *dst, const float *halo, int T, int h, int64_t n,
+                                      int64_t ld, int64_t ld_halo, const float *band_w, int b, int transposed,
+                                      void *stream);
 
 /* ---- (d) facewise SpMM  P_t = A~_t . X_t -----------------------------------
  * ref: the loop ehf:205-207 / ehf:309-311 and compute_AX ehf:301-305, 469-473.
@@ -153,6 +161,14 @@ int tmgcn_gemm_xw_fwd(const float *p, const float *w, float *y, int64_t R, int K
 size_t tmgcn_gemm_dw_ws_bytes(int K, int Nf);
 int tmgcn_gemm_dw_dx_bwd(const float *p, const float *w, const float *y, const float *dy, float *dp, float *dw,
                          int64_t R, int K, int Nf, int act, void *dw_ws, void *stream);
+
+/* per-slice weights (condensed_W=False; ref: ehf:188-191, 222, 277-282, 330): y[t] = act(p[t] . w[t]) with
+ * p (T, N, K), w (T, K, Nf), y (T, N, Nf) -- all T slices per call (one grouped launch on the SIMT path).
+ * bwd: dp[t] = (dy[t] * act'(y[t])) . w[t]^T and dw[t] = p[t]^T . (dy[t] * act'(y[t])); dp or dw may be NULL. */
+int tmgcn_gemm_xw_sliced_fwd(const float *p, const float *w, float *y, int T, int64_t N, int K, int Nf, int act,
+                             void *stream);
+int tmgcn_gemm_sliced_bwd(const float *p, const float *w, const float *y, const float *dy, float *dp, float *dw,
+                          int T, int64_t N, int K, int Nf, int act, void *stream);
 
 /* ---- (e) edge-endpoint gather readout ------------------------------------
  * ref: flat ids ehf:196-198; gather + concat ehf:228-230 / 351-353 / 491-493;

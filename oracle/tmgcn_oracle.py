@@ -209,8 +209,12 @@ def _readout(Y, src, trg, U):
 # --------------------------------------------------------------------------
 def apply_Minv(M, Z):
     """Y = inv(M) @ Z.reshape(T, -1) (ref: ehf:183-184, 223-224).  The reference multiplies its fp64 inv(M)
-    with the fp32 buffer and raises a dtype error on the shipped dtypes [probed]; the only reading that runs is
-    "promote to fp64, round the result back to fp32", which is what this does.  PARITY UNPINNED for this flag."""
+    with the fp32 buffer and raises a dtype error on the shipped fp64 inputs [probed]; this restatement promotes
+    to fp64 and rounds the result back to fp32.  Pinned by tests/golden/minv.npz: the UNMODIFIED reference does
+    run the flag when M, X and the slices are all fp32 (fp32 LAPACK inverse, fp32 matmul), and this function
+    reproduces those outputs and gradients to ~3e-7 (tests/test_oracle_golden.py::test_use_minv_golden).
+    EmbeddingGCN2(use_Minv=True) runs in no dtype configuration of the reference (ehf:335 up-casts to fp64 before
+    the fp32 inv(M)), so the 2-layer composition of this function stays unpinned."""
     Minv = torch.from_numpy(np.linalg.inv(M.numpy()))
     return torch.matmul(Minv, Z.double().reshape(Z.shape[0], -1)).reshape(Z.size()).float()
 

@@ -30,6 +30,11 @@ def golden_models():
 
 
 @pytest.fixture(scope="session")
+def golden_minv():
+    return np.load(os.path.join(GOLDEN, "minv.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_data():
     return np.load(os.path.join(GOLDEN, "data_helpers.npz"))
 

@@ -251,11 +251,76 @@ def gen_models():
         p_.grad = None
     out.backward(dReg)
     d["reg_dW"], d["reg_dlw"], d["reg_dlb"] = m.W.grad.numpy().copy(), m.lin1.weight.grad.numpy().copy(), m.lin1.bias.grad.numpy().copy()
-    # use_Minv=True (ehf:183-184, 223-224) cannot be pinned here: the reference itself raises
-    # "expected m1 and m2 to have the same dtype, but got: double != float" at ehf:224 (fp64 inv(M) times the
-    # fp32 AtXt buffer) on the shipped dtypes, so that flag is checked against the dense-inverse formula instead.
+    # use_Minv=True (ehf:183-184, 223-224): the reference raises "expected m1 and m2 to have the same dtype, but
+    # got: double != float" at ehf:224 (fp64 inv(M) times the fp32 AtXt buffer) on these fp64 inputs; the flag is
+    # pinned by gen_minv() below, which runs the unmodified reference on all-fp32 inputs.
     np.savez_compressed(os.path.join(OUT, "models.npz"), **d)
     print("models.npz", len(d))
+
+
+def gen_minv():
+    """use_Minv=True (ehf:183-184, 223-224, 331-332, 338-341, 415-417).  On the shipped dtypes (fp64 M and X) the
+    reference raises "expected m1 and m2 to have the same dtype" at ehf:224: Minv = t.tensor(np.linalg.inv(M)) is
+    fp64 and multiplies the fp32 AtXt buffer.  The UNMODIFIED reference does run the flag when every input is
+    fp32 (M, X and the slice values): inv(M) is then an fp32 LAPACK inverse and the product an fp32 matmul.
+    That all-fp32 run is what is stored here -- no shim, no edit; only the input dtypes differ from the
+    experiments'.  T = 7, b = 3, un-normalised M (cond ~ 5), so the fp32 inverse is good to ~1e-6."""
+    ns = load_ref_functions(3)
+    T, N, F0, E = 7, 30, 3, 70
+    C = random_coo(T, N, 0.1, 21)
+    M = ns["create_matrix_M"](T, 3)
+    Ct = ns["func_MProduct"](C, M)
+    g = t.Generator().manual_seed(22)
+    X = t.rand(T, N, F0, generator=g, dtype=t.float64)
+    edges = t.stack([t.randint(0, T, (E,), generator=g), t.randint(0, N, (E,), generator=g),
+                     t.randint(0, N, (E,), generator=g)])
+    edges = edges[:, t.argsort(edges[0], stable=True)]
+    dOut = t.randn(E, 2, generator=g)
+    M32, X32 = M.float(), X.float()
+    At32 = []
+    for j in range(T):
+        idx = Ct._indices()[0] == j
+        At32.append(t.sparse.FloatTensor(Ct._indices()[1:3, idx], Ct._values()[idx].float()))
+    d = {"Ct_idx": Ct._indices().numpy(), "Ct_val": Ct._values().numpy(), "M": M.numpy(), "X": X.numpy(),
+         "edges": edges.numpy(), "dOut": dOut.numpy(), "TN": np.array([T, N])}
+    t.manual_seed(800)
+    m = ehf.EmbeddingGCN(At32, X32, edges, M32, hidden_feat=[5, 2], condensed_W=True, use_Minv=True)
+    out = m()
+    d["gcn1_W"], d["gcn1_U"], d["gcn1_out"] = m.W.detach().numpy().copy(), m.U.detach().numpy().copy(), out.detach().numpy()
+    for k, v in grads(m, out, dOut, ["W", "U"]).items():
+        d["gcn1_d" + k] = v
+    t.manual_seed(810)
+    m = ehf.EmbeddingGCN(At32, X32, edges, M32, hidden_feat=[5, 2], condensed_W=False, use_Minv=True)
+    out = m()
+    d["gcn1u_W"], d["gcn1u_U"], d["gcn1u_out"] = m.W.detach().numpy().copy(), m.U.detach().numpy().copy(), out.detach().numpy()
+    for k, v in grads(m, out, dOut, ["W", "U"]).items():
+        d["gcn1u_d" + k] = v
+    t.manual_seed(820)
+    try:
+        m = ehf.EmbeddingGCN2(At32, X32, edges, M32, hidden_feat=[5, 4, 2], condensed_W=True, use_Minv=True,
+                              nonlin2="leaky")
+        out = m()
+        for n in ("W1", "W2", "U"):
+            d["gcn2_" + n] = getattr(m, n).detach().numpy().copy()
+        d["gcn2_out"] = out.detach().numpy()
+        for k, v in grads(m, out, dOut, ["W1", "W2", "U"]).items():
+            d["gcn2_d" + k] = v
+    except RuntimeError as ex:          # layer 2 of the reference up-casts to fp64 (ehf:335) before inv(M)
+        d["gcn2_error"] = np.array(str(ex))
+        print("EmbeddingGCN2(use_Minv=True) cannot run even in fp32:", ex)
+    t.manual_seed(830)
+    m = ehf.EmbeddingGCN_reg(At32, X32, M32, hidden_feat=[5, 2], condensed_W=True, use_Minv=True)
+    out = m()
+    dReg = t.randn(out.shape, generator=g)
+    d["reg_W"], d["reg_lw"], d["reg_lb"] = (m.W.detach().numpy().copy(), m.lin1.weight.detach().numpy().copy(),
+                                            m.lin1.bias.detach().numpy().copy())
+    d["reg_out"], d["reg_dOut"] = out.detach().numpy(), dReg.numpy()
+    for p_ in m.parameters():
+        p_.grad = None
+    out.backward(dReg)
+    d["reg_dW"] = m.W.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "minv.npz"), **d)
+    print("minv.npz", len(d))
 
 
 def gen_preprocess():
@@ -376,6 +441,10 @@ def gen_data_helpers():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "minv":       # only the newest fixture (the others are unchanged)
+        gen_minv()
+        sys.exit(0)
+    gen_minv()
     gen_data_helpers()
     gen_preprocess()
     gen_mproduct()

@@ -325,7 +325,7 @@ def test_gemm_fwd_bwd(tg, R, K, Nf, act):
 # --------------------------------------------------------------------------
 # (e) edge readout
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("F,Cc", [(2, 2), (6, 3), (16, 1), (128, 2), (100, 8)])
+@pytest.mark.parametrize("F,Cc", [(2, 2), (6, 3), (16, 1), (128, 2), (100, 8), (12, 11), (64, 40)])
 def test_edge_readout_and_gather(tg, F, Cc):
     from tmgcn_b200 import ops
     T, N, E = 5, 60, 700
@@ -512,6 +512,30 @@ def test_module_per_slice_weights_and_regression_head(tg, golden_models):
     assert relerr(r.lin1.weight.grad, g["reg_dlw"]) <= TOL_GRAD and relerr(r.lin1.bias.grad, g["reg_dlb"]) <= TOL_GRAD
 
 
+@pytest.mark.parametrize("K,Nf,act", [(2, 6, "none"), (6, 6, "selu"), (70, 33, "relu"), (128, 128, "leaky")])
+def test_gemm_xw_sliced_grouped_launch(tg, K, Nf, act):
+    """condensed_W=False (ehf:188-191): y[t] = act(p[t] @ w[t]) for all slices in one grouped launch, with
+    dP and per-slice dW, against torch fp64."""
+    from tmgcn_b200 import _lib, ops
+    T, N = 7, 150
+    g = torch.Generator().manual_seed(K + Nf)
+    p = torch.randn(T, N, K, generator=g)
+    w = torch.randn(T, K, Nf, generator=g) / K ** 0.5
+    dy = torch.randn(T, N, Nf, generator=g)
+    pr, wr = p.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = oracle.nonlin(act)(torch.matmul(pr, wr))
+    ref.backward(dy.double())
+    pd, wd = p.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    n0 = _lib.launch_count()
+    out = ops.gemm_xw_sliced(pd, wd, act)
+    n_fwd = _lib.launch_count() - n0
+    out.backward(dy.cuda())
+    if not (K == 128 and Nf == 128):
+        assert n_fwd == 1                         # one grouped launch, not one per slice
+    assert relerr(out, ref) <= TOL_OUT
+    assert relerr(pd.grad, pr.grad) <= TOL_GRAD and relerr(wd.grad, wr.grad) <= TOL_GRAD
+
+
 def test_module_use_minv(tg, golden_models):
     """use_Minv=True (ehf:183-184, 223-224, 331-341): inv(M) applied as a banded substitution."""
     from tmgcn_b200 import ops
@@ -549,6 +573,65 @@ def test_module_use_minv(tg, golden_models):
     out_r.backward(dOut.cpu())
     for n in ("W1", "W2", "U"):
         assert relerr(getattr(m2, n).grad, getattr(ref2, n).grad) <= TOL_GRAD, n
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_solve_part_chained_blocks(tg, transposed):
+    """the time-sharded / column-chunked substitution kernel (tmgcn_mtransform_dense_solve_part): three uneven
+    time blocks chained on one GPU through their halo rows, three column chunks each, against inv(M)."""
+    from tmgcn_b200 import sharding
+    T, b, N, F = 41, 6, 33, 5
+    M = oracle.create_matrix_M(T, b, normalize=True)
+    band = tg.Band(M)
+    Z = torch.randn(T, N, F, generator=torch.Generator().manual_seed(4))
+    Minv = torch.linalg.inv(M)
+    want = ((Minv.T if transposed else Minv) @ Z.double().reshape(T, -1)).reshape(Z.shape)
+    blocks = [(0, 9), (9, 27), (27, 41)]
+    order = blocks[::-1] if transposed else blocks
+    NF, h = N * F, b - 1
+    out = torch.empty(T, NF, device="cuda")
+    Zd = Z.cuda().reshape(T, NF)
+    halo = None
+    for t0, t1 in order:
+        Tl = t1 - t0
+        rows_w = min(T, t1 + h) if transposed else t1
+        w = band.device_weights(t0, rows_w, torch.float32)
+        z, y = Zd[t0:t1].contiguous(), torch.empty(Tl, NF, device="cuda")
+        for c in range(3):
+            c0, c1 = NF * c // 3, NF * (c + 1) // 3
+            hk = 0 if halo is None else h
+            hc = None if halo is None else halo[:, c0:c1].contiguous()
+            sharding._device_local_solve(z[:, c0:], y[:, c0:], hc, Tl, hk, c1 - c0, NF, c1 - c0, w, b, transposed)
+        out[t0:t1] = y
+        halo = y[:h].clone() if transposed else y[Tl - h:].clone()
+    assert relerr(out.reshape(T, N, F), want) <= TOL_OUT
+
+
+def test_module_use_minv_golden(tg, golden_minv):
+    """use_Minv=True against the UNMODIFIED reference (run on all-fp32 inputs, the one dtype configuration in
+    which it executes the flag: tests/golden/make_golden.py::gen_minv): 1-layer with shared and per-slice
+    weights (ehf:222-224) and the regression head (ehf:415-417)."""
+    g = golden_minv
+    T, N = (int(x) for x in g["TN"])
+    M, X, edges = torch.from_numpy(g["M"]), torch.from_numpy(g["X"]), torch.from_numpy(g["edges"])
+    At = [a.coalesce() for a in oracle.split_slices(g["Ct_idx"], g["Ct_val"], T, N)]
+    dOut = torch.from_numpy(g["dOut"]).cuda()
+    for tag, cw in (("gcn1", True), ("gcn1u", False)):
+        m = tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[5, 2], condensed_W=cw, use_Minv=True)
+        _load(m, g, tag + "_", ["W", "U"])
+        out = m()
+        assert relerr(out, g[tag + "_out"]) <= TOL_OUT, tag
+        out.backward(dOut)
+        assert relerr(m.W.grad, g[tag + "_dW"]) <= TOL_GRAD and relerr(m.U.grad, g[tag + "_dU"]) <= TOL_GRAD, tag
+    r = tg.EmbeddingGCN_reg(At, X, M, hidden_feat=[5, 2], condensed_W=True, use_Minv=True)
+    with torch.no_grad():
+        r.W.copy_(torch.from_numpy(g["reg_W"]))
+        r.lin1.weight.copy_(torch.from_numpy(g["reg_lw"]))
+        r.lin1.bias.copy_(torch.from_numpy(g["reg_lb"]))
+    out = r()
+    assert relerr(out, g["reg_out"]) <= TOL_OUT
+    out.backward(torch.from_numpy(g["reg_dOut"]).cuda())
+    assert relerr(r.W.grad, g["reg_dW"]) <= TOL_GRAD
 
 
 def test_module_errors(tg, golden_models):

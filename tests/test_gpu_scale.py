@@ -89,6 +89,64 @@ def test_config_shapes_vs_oracle(tg, name, N, T, m, b):
         assert relerr(getattr(m_gpu, n).grad, getattr(m_ref, n).grad) <= TOL_GRAD, n
 
 
+def test_c4_shape_layer_vs_oracle(tg):
+    """BASELINE.json configs[3] (Reddit shape: N = 55 863, b = 20, F = 128, experiment_reddit_our.py:31) with T cut
+    to 44 slices -- what the CPU restatement does in seconds -- through the planned layer step: once as a single
+    shard and once as the two time blocks of a 2-rank run chained on this GPU (halo = b-1 = 19 slices, the
+    nearly-all-halo regime of C4 on 8 GPUs), both against the oracle's forward and backward."""
+    from tmgcn_b200 import ops, synth
+    from tmgcn_b200.layer_step import LayerStep
+    N, T, m, b, F, C = 55_863, 44, 32_000, 20, 128, 2
+    idx, val = synth.synth_coo(N, T, m, 0.9, seed=20261017)
+    M = oracle.create_matrix_M(T, b)
+    band = tg.Band(M)
+    ref_idx, ref_val = oracle.func_MProduct(idx.numpy(), val.numpy(), (T, N, N), M.numpy(), no_diag=b)
+    A = tg.SliceCSR.from_coo(idx, val, T, N)
+    At = ops.mtransform_sparse(A, band)
+    oi, ov = At.to_coo()
+    assert torch.equal(oi.cpu(), torch.from_numpy(ref_idx))
+    g = torch.Generator().manual_seed(5)
+    H = torch.rand(T, N, F, generator=g)
+    W = torch.randn(F, F, generator=g) / F ** 0.5
+    U = torch.randn(2 * F, C, generator=g)
+    E = 60_000
+    pick = torch.sort(torch.randint(0, ref_idx.shape[1], (E,), generator=g)).values
+    edges = torch.from_numpy(ref_idx[:, pick.numpy()])
+    dOut = torch.randn(E, C, generator=g)
+    out_r, dH_r, dW_r, dU_r = oracle.layer_fwd_bwd(oracle.split_slices(ref_idx, ref_val, T, N), H, M, W, U, edges,
+                                                   dOut, "none", as_reference=False)
+    Wd, Ud = W.cuda(), U.cuda()
+    for mode in ("lowrank", "dense"):
+        step = LayerStep(At, band, tg.EdgePlan(edges, N, T=T), F, F, C, "none", bwd_mode=mode)
+        out = step.forward(H.cuda(), Wd, Ud)
+        assert relerr(out, out_r) <= TOL_OUT, mode
+        dH, dW, dU = step.backward(dOut.cuda(), Wd, Ud)
+        assert relerr(dH, dH_r) <= TOL_GRAD and relerr(dW, dW_r) <= TOL_GRAD and relerr(dU, dU_r) <= TOL_GRAD, mode
+        del step
+    # two time blocks [0, 22) and [22, 44): the second holds a 19-slice halo of A and H; its halo gradient is
+    # what a rank would send back to its predecessor
+    t_cut, halo = 22, b - 1
+    outs, dHs, dWs, dUs = [], torch.zeros(T, N, F), [], []
+    for (t0, t1, h) in ((0, t_cut, 0), (t_cut, T, halo)):
+        sel = (idx[0] >= t0 - h) & (idx[0] < t1)
+        sub = idx[:, sel].clone()
+        sub[0] -= t0 - h
+        A_in = tg.SliceCSR.from_coo(sub, val[sel], t1 - t0 + h, N)
+        At_b = ops.mtransform_sparse(A_in, band, t0, t1, h)
+        esel = (edges[0] >= t0) & (edges[0] < t1)
+        plan = tg.EdgePlan(edges[:, esel], N, t_offset=t0, T=t1 - t0)
+        step = LayerStep(At_b, band, plan, F, F, C, "none", t0, t1, h, bwd_mode="dense")
+        outs.append(step.forward(H[t0 - h:t1].cuda().contiguous(), Wd, Ud).cpu())
+        dH, dW, dU = step.backward(dOut[esel].cuda().contiguous(), Wd, Ud)
+        dHs[t0 - h:t1] += dH.cpu()
+        dWs.append(dW.cpu().double())
+        dUs.append(dU.cpu().double())
+        del step, At_b, A_in
+    assert relerr(torch.cat(outs), out_r) <= TOL_OUT
+    assert relerr(dHs, dH_r) <= TOL_GRAD
+    assert relerr(dWs[0] + dWs[1], dW_r) <= TOL_GRAD and relerr(dUs[0] + dUs[1], dU_r) <= TOL_GRAD
+
+
 # --------------------------------------------------------------------------
 # benchmark-scale properties (N = 2M, F = 128)
 # --------------------------------------------------------------------------

@@ -184,3 +184,25 @@ def test_mproduct_sparse_equals_dense_on_random_bands():
         got[tuple(i_s)] = v_s
         np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-15)
     run()
+
+
+@pytest.mark.parametrize("tag", ["gcn1", "gcn1u"])
+def test_use_minv_golden(golden_minv, tag):
+    """use_Minv=True (ehf:183-184, 223-224): the oracle against the unmodified reference run on all-fp32 inputs
+    (the only dtype configuration in which the reference executes that flag; make_golden.py::gen_minv).  The
+    reference inverts M and accumulates in fp32, the oracle in fp64: 2e-6 covers that."""
+    g = golden_minv
+    T, N = (int(x) for x in g["TN"])
+    M, X, edges = torch.from_numpy(g["M"]), torch.from_numpy(g["X"]), torch.from_numpy(g["edges"])
+    At = oracle.split_slices(g["Ct_idx"], g["Ct_val"], T, N)
+    m = oracle.OracleGCN(At, X, edges, M, torch.from_numpy(g[tag + "_W"]), torch.from_numpy(g[tag + "_U"]),
+                         as_reference=False, use_Minv=True)
+    out = m()
+    out.backward(torch.from_numpy(g["dOut"]))
+
+    def rel(a, b):
+        a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+        return ((a - b).abs().max() / b.abs().max()).item()
+    assert rel(out.detach(), g[tag + "_out"]) <= 2e-6
+    assert rel(m.W.grad, g[tag + "_dW"]) <= 2e-6 and rel(m.U.grad, g[tag + "_dU"]) <= 2e-6
+    assert "same dtype" in str(g["gcn2_error"])          # the 2-layer model cannot run the flag at all

@@ -37,12 +37,15 @@ PROTOTYPES = {
     "tmgcn_mtransform_dense_bwd": (_i, [_p, _p, _i, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_solve_fwd": (_i, [_p, _p, _i, _l, _p, _i, _p]),
     "tmgcn_mtransform_dense_solve_bwd": (_i, [_p, _p, _i, _l, _p, _i, _p]),
+    "tmgcn_mtransform_dense_solve_part": (_i, [_p, _p, _p, _i, _i, _l, _l, _l, _p, _i, _i, _p]),
     "tmgcn_mtransform_dense_fwd_split": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _i, _p]),
     "tmgcn_mtransform_dense_bwd_range": (_i, [_p, _p, _i, _i, _l, _p, _i, _i, _i, _p]),
     "tmgcn_spmm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _l, _i, _i, _p]),
     "tmgcn_gemm_xw_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),
     "tmgcn_gemm_dw_ws_bytes": (_z, [_i, _i]),
     "tmgcn_gemm_dw_dx_bwd": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
+    "tmgcn_gemm_xw_sliced_fwd": (_i, [_p, _p, _p, _i, _l, _i, _i, _i, _p]),
+    "tmgcn_gemm_sliced_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p]),
     "tmgcn_flat_edge_ids": (_i, [_p, _l, _l, _l, _p, _p, _p]),
     "tmgcn_edge_gather_fwd": (_i, [_p, _p, _p, _p, _l, _i, _p]),
     "tmgcn_edge_readout_fwd": (_i, [_p, _p, _p, _p, _p, _l, _i, _i, _p]),

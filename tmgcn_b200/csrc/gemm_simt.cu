@@ -19,9 +19,15 @@ constexpr int BM = 64, BN = 64, BK = 16;
 template <bool TRANSB, bool GRAD>
 __global__ void __launch_bounds__(256) sgemm_rows(const float *__restrict__ A, const float *__restrict__ Yaux,
                                                   const float *__restrict__ B, float *__restrict__ C, int64_t R,
-                                                  int Kd, int Nc, int act) {
+                                                  int Kd, int Nc, int act, int64_t strideA = 0, int64_t strideB = 0,
+                                                  int64_t strideC = 0) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
+    // grouped form (per-slice weights, ehf:188-191): blockIdx.z selects the slice, every operand advances by its stride
+    A += (int64_t)blockIdx.z * strideA;
+    if (GRAD) Yaux += (int64_t)blockIdx.z * strideA;
+    B += (int64_t)blockIdx.z * strideB;
+    C += (int64_t)blockIdx.z * strideC;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t row0 = (int64_t)blockIdx.x * BM;
@@ -136,6 +142,64 @@ __global__ void __launch_bounds__(256) dw_partial(const float *__restrict__ P, c
     }
 }
 
+// per-slice dW[t] = P[t]^T . (dY[t] * act'(Y[t])): one CTA per (slice, 64 x 64 tile of dW) walks all N rows of its
+// slice in a fixed order (deterministic, no partials); used by the per-slice-weights path only
+__global__ void __launch_bounds__(256) dw_grouped(const float *__restrict__ P, const float *__restrict__ Y,
+                                                  const float *__restrict__ dY, float *__restrict__ dW, int64_t N,
+                                                  int K, int Nf, int act) {
+    __shared__ float Ps[BK][BM + 4];
+    __shared__ float Ds[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t t = blockIdx.x;
+    const int k0 = blockIdx.y * BM, n0 = blockIdx.z * BN;
+    P += t * N * K;
+    dY += t * N * Nf;
+    if (Y) Y += t * N * Nf;
+    float acc[4][4] = {};
+    for (int64_t r0 = 0; r0 < N; r0 += BK) {
+        for (int idx = tid; idx < BK * BM; idx += 256) {
+            const int rr = idx / BM, k = idx % BM;
+            Ps[rr][k] = (r0 + rr < N && k0 + k < K) ? P[(r0 + rr) * K + k0 + k] : 0.f;
+        }
+        for (int idx = tid; idx < BK * BN; idx += 256) {
+            const int rr = idx / BN, n = idx % BN;
+            float v = 0.f;
+            if (r0 + rr < N && n0 + n < Nf) {
+                const int64_t o = (r0 + rr) * Nf + n0 + n;
+                v = dY[o];
+                if (act != TMGCN_ACT_NONE) v *= act_grad_rt(Y[o], act);
+            }
+            Ds[rr][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < BK; ++rr) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Ps[rr][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Ds[rr][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *out = dW + t * (int64_t)K * Nf;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty * 4 + i;
+        if (k >= K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < Nf) out[(int64_t)k * Nf + n] = acc[i][j];
+        }
+    }
+}
+
 // fixed-order reduction of the per-chunk partials: deterministic dW
 __global__ void reduce_partials(const float *__restrict__ partial, float *__restrict__ out, int n_chunks,
                                 int64_t n_elem) {
@@ -191,6 +255,30 @@ int gemm_simt_dw(const float *p, const float *y, const float *dy, float *dw, int
     const int64_t n_elem = (int64_t)K * Nf;
     reduce_partials<<<(unsigned)ceil_div(n_elem, 256), 256, 0, st>>>(ws, dw, (int)n_chunks, n_elem);
     return after_launch("reduce_partials");
+}
+
+// ---- per-slice weights (condensed_W=False, ref: ehf:188-191, 222, 277-282, 330): all T slices in one launch ----
+int gemm_simt_sliced_fwd(const float *p, const float *w, float *y, int T, int64_t N, int K, int Nf, int act,
+                         cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(N, BM), (unsigned)ceil_div(Nf, BN), (unsigned)T);
+    sgemm_rows<false, false><<<grid, 256, 0, st>>>(p, nullptr, w, y, N, K, Nf, act, N * K, (int64_t)K * Nf, N * Nf);
+    return after_launch("sgemm_rows<sliced fwd>");
+}
+int gemm_simt_sliced_dp(const float *w, const float *y, const float *dy, float *dp, int T, int64_t N, int K, int Nf,
+                        int act, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(N, BM), (unsigned)ceil_div(K, BN), (unsigned)T);
+    if (act == TMGCN_ACT_NONE)
+        sgemm_rows<true, false><<<grid, 256, 0, st>>>(dy, nullptr, w, dp, N, Nf, K, TMGCN_ACT_NONE, N * Nf,
+                                                      (int64_t)K * Nf, N * K);
+    else
+        sgemm_rows<true, true><<<grid, 256, 0, st>>>(dy, y, w, dp, N, Nf, K, act, N * Nf, (int64_t)K * Nf, N * K);
+    return after_launch("sgemm_rows<sliced dP>");
+}
+int gemm_simt_sliced_dw(const float *p, const float *y, const float *dy, float *dw, int T, int64_t N, int K, int Nf,
+                        int act, cudaStream_t st) {
+    dim3 grid((unsigned)T, (unsigned)ceil_div(K, BM), (unsigned)ceil_div(Nf, BN));
+    dw_grouped<<<grid, 256, 0, st>>>(p, y, dy, dw, N, K, Nf, act);
+    return after_launch("dw_grouped");
 }
 
 }  // namespace tmgcn

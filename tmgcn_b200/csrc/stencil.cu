@@ -142,23 +142,35 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
 // fp64 registers (loads / stores fp32) so the feedback does not amplify rounding over hundreds of slices.
 // TRANSPOSED solves M^T x_3 g_in = g_out (the adjoint), marching downwards:
 //   g_in[s] = (g_out[s] - sum_{i>=1} M[s+i, s] g_in[s+i]) / M[s,s].
+// Time-sharded form: the rank's block continues a recurrence that started on another rank, so the ring starts
+// from `h` halo rows -- the predecessor's last h OUTPUTS (forward) or the successor's first h outputs
+// (transposed) -- instead of zeros, and the weight table of the transposed solve reaches h rows past the block
+// (M[s+i, s] with s+i owned by the successor).  Rows are `ld` floats apart so a caller can pipeline the
+// cross-rank scan over column chunks (sharding.solve_pipelined).
 template <int B, bool TRANSPOSED>
-__global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ src, float *__restrict__ dst, int T,
-                                                    int64_t n, const float *__restrict__ band_w, int b) {
+__global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                    const float *__restrict__ halo, int T, int h, int64_t n,
+                                                    int64_t ld, int64_t ld_halo, const float *__restrict__ band_w,
+                                                    int b) {
     extern __shared__ float sw[];
-    load_weights<B>(sw, band_w, T, b);
+    load_weights<B>(sw, band_w, TRANSPOSED ? T + h : T, b);
     const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n) return;
     double ring[B];
 #pragma unroll
     for (int k = 0; k < B; ++k) ring[k] = 0.0;
+    // ring[j] holds the output of the step u with u = j (mod B); step -i (i = 1..h) is the i-th halo row
+    // counted from the block: forward y[-i] = halo[h - i], transposed g[T - 1 + i] = halo[i - 1]
+#pragma unroll
+    for (int i = 1; i < B; ++i)
+        if (i <= h) ring[B - i] = (double)__ldg(halo + (int64_t)(TRANSPOSED ? i - 1 : h - i) * ld_halo + pos);
     for (int u0 = 0; u0 < T; u0 += B) {
 #pragma unroll
         for (int k = 0; k < B; ++k) {
             const int u = u0 + k;
             if (u < T) {
                 const int t = TRANSPOSED ? T - 1 - u : u;
-                double acc = (double)__ldg(src + (int64_t)t * n + pos);
+                double acc = (double)__ldg(src + (int64_t)t * ld + pos);
 #pragma unroll
                 for (int i = 1; i < B; ++i) {
                     // forward: M[t, t-i] = sw[(t+B)*B + i];  transposed: M[t+i, t] = sw[(t+i+B)*B + i]
@@ -167,27 +179,31 @@ __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ sr
                 }
                 acc /= (double)sw[(t + B) * B];
                 ring[k] = acc;
-                dst[(int64_t)t * n + pos] = (float)acc;
+                dst[(int64_t)t * ld + pos] = (float)acc;
             }
         }
     }
 }
 
 template <bool TRANSPOSED>
-static int solve_entry(const float *z, float *y, int T, int64_t NF, const float *band_w, int b, void *stream) {
-    TMGCN_REQUIRE(T >= 0 && NF >= 0, "mtransform_dense_solve: negative size");
+static int solve_entry(const float *z, float *y, const float *halo, int T, int h, int64_t n, int64_t ld,
+                       int64_t ld_halo, const float *band_w, int b, void *stream) {
+    TMGCN_REQUIRE(T >= 0 && n >= 0 && h >= 0, "mtransform_dense_solve: negative size");
     TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform_dense_solve: band width b=%d outside [1, 32]", b);
-    if (NF == 0 || T == 0) return 0;
-    TMGCN_REQUIRE(z && y && band_w, "mtransform_dense_solve: null pointer");
+    TMGCN_REQUIRE(h <= b - 1, "mtransform_dense_solve: halo=%d exceeds b-1=%d", h, b - 1);
+    TMGCN_REQUIRE(ld >= n && (h == 0 || ld_halo >= n), "mtransform_dense_solve: row stride smaller than the row");
+    if (n == 0 || T == 0) return 0;
+    TMGCN_REQUIRE(z && y && band_w && (h == 0 || halo), "mtransform_dense_solve: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    const int T_tab = TRANSPOSED ? T + h : T;
 #define TMGCN_SOLVE(BB)                                                                                     \
     if (b <= BB) {                                                                                          \
-        const size_t smem = (size_t)(T + 2 * BB) * BB * sizeof(float);                                      \
+        const size_t smem = (size_t)(T_tab + 2 * BB) * BB * sizeof(float);                                  \
         TMGCN_REQUIRE(smem <= 200 * 1024, "mtransform_dense_solve: T=%d too large for the weight table", T); \
         auto kern = solve_kernel<BB, TRANSPOSED>;                                                           \
         if (smem > 48 * 1024)                                                                               \
             TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<(unsigned)ceil_div(NF, 256), 256, smem, st>>>(z, y, T, NF, band_w, b);                       \
+        kern<<<(unsigned)ceil_div(n, 256), 256, smem, st>>>(z, y, halo, T, h, n, ld, ld_halo, band_w, b);   \
         return after_launch(TRANSPOSED ? "solve_bwd" : "solve_fwd");                                        \
     }
     TMGCN_SOLVE(2)
@@ -286,11 +302,17 @@ int tmgcn_mtransform_dense_bwd(const float *g_out, float *g_in, int T_out, int h
 }
 int tmgcn_mtransform_dense_solve_fwd(const float *z, float *y, int T, int64_t NF, const float *band_w, int b,
                                      void *stream) {
-    return tmgcn::solve_entry<false>(z, y, T, NF, band_w, b, stream);
+    return tmgcn::solve_entry<false>(z, y, nullptr, T, 0, NF, NF, NF, band_w, b, stream);
 }
 int tmgcn_mtransform_dense_solve_bwd(const float *g_y, float *g_z, int T, int64_t NF, const float *band_w, int b,
                                      void *stream) {
-    return tmgcn::solve_entry<true>(g_y, g_z, T, NF, band_w, b, stream);
+    return tmgcn::solve_entry<true>(g_y, g_z, nullptr, T, 0, NF, NF, NF, band_w, b, stream);
+}
+int tmgcn_mtransform_dense_solve_part(const float *src, float *dst, const float *halo, int T, int h, int64_t n,
+                                      int64_t ld, int64_t ld_halo, const float *band_w, int b, int transposed,
+                                      void *stream) {
+    if (transposed) return tmgcn::solve_entry<true>(src, dst, halo, T, h, n, ld, ld_halo, band_w, b, stream);
+    return tmgcn::solve_entry<false>(src, dst, halo, T, h, n, ld, ld_halo, band_w, b, stream);
 }
 int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
                                      const float *band_w, int b, int s_begin, int s_end, void *stream) {

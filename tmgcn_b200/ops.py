@@ -592,6 +592,11 @@ class _PropagateLinearReadout(torch.autograd.Function):
 
 def propagate_linear_readout(H, W, U, csr, band, plan):
     """Differentiable fused linear layer + readout; csr / band may be None (skip SpMM / M-transform)."""
+    if U.shape[1] > MAX_FUSED_CLASSES:
+        # many classes: the factor kernels hold at most 8 class accumulators -- plain composition of the stages
+        Ht = mtransform_dense(H, band) if band is not None else H
+        P = spmm(csr, Ht) if csr is not None else Ht
+        return edge_readout(gemm_xw(P, W), U, plan)
     return _PropagateLinearReadout.apply(H, W, U, csr, band, plan)
 
 
@@ -617,15 +622,50 @@ def gemm_xw(p, w, act=None):
     return _Gemm.apply(p, w, ACT[act] if not isinstance(act, int) else act)
 
 
+class _GemmSliced(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, w, act):
+        lib = _lib.load()
+        p, w = _f32(p), _f32(w)
+        T, N, K = p.shape
+        Nf = w.shape[2]
+        y = torch.empty(T, N, Nf, dtype=torch.float32, device=p.device)
+        _lib.check(lib.tmgcn_gemm_xw_sliced_fwd(_p(p, _F), _p(w, _F), _p(y, _F), T, N, K, Nf, act, _stream()))
+        ctx.act = act
+        ctx.save_for_backward(p, w, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        p, w, y = ctx.saved_tensors
+        g = _f32(g)
+        T, N, K = p.shape
+        Nf = w.shape[2]
+        dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.tmgcn_gemm_sliced_bwd(_p(p, _F), _p(w, _F), _p(y), _p(g, _F), _p(dp), _p(dw), T, N, K, Nf,
+                                             ctx.act, _stream()))
+        return dp, dw, None
+
+
 def gemm_xw_sliced(p, w, act=None):
     """per-slice weights: act(p[t] @ w[t]) for w of shape (T, K, Nf) -- the reference's condensed_W=False
-    batched matmul (ref: ehf:188-191, 222, 277-282, 330); one GEMM launch per slice, differentiable."""
-    assert p.dim() == 3 and w.dim() == 3 and p.shape[0] == w.shape[0]
-    return torch.stack([gemm_xw(p[t], w[t], act) for t in range(p.shape[0])])
+    batched matmul (ref: ehf:188-191, 222, 277-282, 330); all slices in one grouped launch (forward, dP and
+    dW each), differentiable."""
+    assert p.dim() == 3 and w.dim() == 3 and p.shape[0] == w.shape[0] and p.shape[2] == w.shape[1]
+    return _GemmSliced.apply(p, w, ACT[act] if not isinstance(act, int) else act)
+
+
+MAX_FUSED_CLASSES = 8     # the fused readout kernels keep the C class accumulators in registers
 
 
 def edge_readout(y, u, plan: EdgePlan):
-    """[y[src] || y[dst]] @ u (ref: ehf:228-232), differentiable."""
+    """[y[src] || y[dst]] @ u (ref: ehf:228-232), differentiable.  Up to 8 classes the classifier is folded into
+    the gather (the (E, 2F) concat is never written); wider classifiers take the gather kernel followed by the
+    feature GEMM, the reference's own two steps (ehf:228-230, 232)."""
+    if u.shape[1] > MAX_FUSED_CLASSES:
+        return gemm_xw(edge_gather(y, plan), u)
     return _Readout.apply(y, u, plan)
 
 

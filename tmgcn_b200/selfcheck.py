@@ -111,5 +111,21 @@ def multi_gpu_parity(rank: int, world: int, dev, acts: Sequence[str] = ("relu", 
         entry["ok"] = (r[0] <= 1e-5 and max(r[1], r[2], r[3]) <= 1e-4 and r[5] == 0.0 and r[6] == 0.0)
         result[str(act)] = entry
         result["ok"] = result["ok"] and entry["ok"]
+    # use_Minv across ranks: the pipelined cross-rank substitution (forward and adjoint) against the
+    # single-GPU solve of the whole tensor
+    Zs = torch.randn(T, N, 8, generator=g).to(dev)
+    full_fwd = ops._Solve.apply(Zs, band)
+    gz = torch.empty_like(Zs)
+    from . import _lib
+    _lib.check(_lib.load().tmgcn_mtransform_dense_solve_bwd(ops._p(Zs), ops._p(gz), T, Zs[0].numel(),
+                                                            ops._p(band.device_weights(0, T, torch.float32)), b,
+                                                            ops._stream()))
+    e_f = _rel(sharding.solve_pipelined(Zs[t0:t1].contiguous(), band, t0, t1, rank, world), full_fwd[t0:t1])
+    e_b = _rel(sharding.solve_pipelined(Zs[t0:t1].contiguous(), band, t0, t1, rank, world, transposed=True), gz[t0:t1])
+    red = torch.tensor([e_f, e_b], device=dev, dtype=torch.float64)
+    dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    e_f, e_b = (float(x) for x in red.tolist())
+    result["use_minv_pipelined_solve"] = {"rel_err_fwd": e_f, "rel_err_adjoint": e_b, "ok": max(e_f, e_b) <= 1e-5}
+    result["ok"] = result["ok"] and result["use_minv_pipelined_solve"]["ok"]
     result["tolerance"] = {"out": 1e-5, "grads": 1e-4}
     return result

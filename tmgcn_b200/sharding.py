@@ -274,6 +274,91 @@ class PeerHalo:
         torch.cuda.current_stream().wait_event(self.reads_done)
 
 
+def _device_local_solve(src, dst, halo, T, h, n, ld, ld_halo, w, b, transposed):
+    """one column chunk of the banded substitution on the device (C ABI: tmgcn_mtransform_dense_solve_part)"""
+    from . import _lib
+    from .ops import _p, _stream
+    lib = _lib.load()
+    _lib.check(lib.tmgcn_mtransform_dense_solve_part(_p(src), _p(dst), _p(halo) if h > 0 else None, T, h, n, ld,
+                                                     ld_halo, _p(w), b, 1 if transposed else 0, _stream()))
+
+
+def solve_pipelined(z: torch.Tensor, band, t0: int, t1: int, rank: int, world: int, transposed: bool = False,
+                    chunks: int = 8, local_solve=None) -> torch.Tensor:
+    """Y = inv(M) x_3 Z (ref: ehf:223-224) -- or the adjoint solve with M^T -- on a time-sharded tensor.
+
+    The substitution y[t] = (z[t] - sum_i M[t,t-i] y[t-i]) / M[t,t] is a recurrence through time, so rank r can
+    only start once rank r-1 has produced its last b-1 output slices: a cross-rank scan.  It is pipelined over
+    `chunks` column ranges of the N*F columns: rank r solves chunk c as soon as the halo of chunk c has
+    arrived and sends its own last b-1 rows of chunk c on while it works on chunk c+1, so G ranks take
+    (G + chunks - 1) / chunks block-times instead of G.  The transposed solve runs the same way from the last
+    rank down.  z: this rank's (T_own, ...) block [t0, t1); returns y of the same shape.  `local_solve` is the
+    per-chunk kernel (default: the device kernel through the C ABI; the CPU tests inject a torch one)."""
+    T_own = t1 - t0
+    assert z.shape[0] == T_own and z.is_contiguous()
+    b = band.b
+    h = b - 1
+    NF = z[0].numel() if T_own else 0
+    y = torch.empty_like(z)
+    cuda = z.is_cuda
+    solve = local_solve or _device_local_solve
+    up, down = (rank + 1, rank - 1) if transposed else (rank - 1, rank + 1)     # halo comes from `up`, goes to `down`
+    has_up = 0 <= up < world and h > 0
+    has_down = 0 <= down < world and h > 0
+    if world > 1:
+        assert_single_hop(T_own, h, world, z.device)
+    # the transposed solve reaches b-1 weight rows into the successor's block (M[s+i, s])
+    rows_w = min(band.T, t1 + h) if transposed else t1
+    if cuda:
+        w = band.device_weights(t0, rows_w, torch.float32)
+    else:
+        w = band.w[t0:rows_w].to(torch.float32).contiguous()
+    h_w = rows_w - t1 if transposed else 0
+    bounds = [NF * c // chunks for c in range(chunks + 1)]
+    cols = [(bounds[c], bounds[c + 1]) for c in range(chunks) if bounds[c + 1] > bounds[c]]
+    z2, y2 = z.view(T_own, NF), y.view(T_own, NF)
+    halo_in = [torch.empty(h, c1 - c0, dtype=z.dtype, device=z.device) for c0, c1 in cols] if has_up else None
+    stage = [torch.empty(h, c1 - c0, dtype=z.dtype, device=z.device) for c0, c1 in cols] if has_down else None
+    if cuda:
+        main = torch.cuda.current_stream()
+        rs, ss = torch.cuda.Stream(device=z.device), torch.cuda.Stream(device=z.device)
+        ev_recv = [torch.cuda.Event() for _ in cols]
+        ev_done = [torch.cuda.Event() for _ in cols]
+        ev_start = torch.cuda.Event()
+        ev_start.record(main)
+        if has_up:                                  # every receive is posted up front, in chunk order
+            with torch.cuda.stream(rs):
+                rs.wait_event(ev_start)
+                for k in range(len(cols)):
+                    dist.recv(halo_in[k], up)
+                    ev_recv[k].record(rs)
+    for k, (c0, c1) in enumerate(cols):
+        if has_up:
+            if cuda:
+                main.wait_event(ev_recv[k])
+            else:
+                dist.recv(halo_in[k], up)
+        hk = h if has_up else 0
+        # transposed on the last rank / forward on rank 0: no halo, the recurrence starts from zeros
+        solve(z2[:, c0:], y2[:, c0:], halo_in[k] if has_up else None, T_own, hk, c1 - c0, NF, c1 - c0, w, b,
+              transposed)
+        if has_down:
+            if cuda:
+                ev_done[k].record(main)
+                with torch.cuda.stream(ss):
+                    ss.wait_event(ev_done[k])
+                    stage[k].copy_(y2[:h, c0:c1] if transposed else y2[T_own - h:, c0:c1])
+                    dist.send(stage[k], down)
+            else:
+                stage[k].copy_(y2[:h, c0:c1] if transposed else y2[T_own - h:, c0:c1])
+                dist.send(stage[k], down)
+    if cuda:
+        main.wait_stream(ss)                        # the staging buffers die with this call
+        main.wait_stream(rs)
+    del h_w
+    return y
+
+
 def allreduce_grads(grads: List[torch.Tensor]):
     """Sum the shared-parameter gradients (dW, dU) over ranks."""
     if not grads:
