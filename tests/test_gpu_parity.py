@@ -155,18 +155,20 @@ for b in (2, 5, 10, 24):
               repr(float((out.val.double() * w).sum())))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for flag in ("0", "1", "2", "4", None, "tiled"):
+    for flag in ("0", "1", "2", "4", None, "tiled", "untiled"):
         env = dict(os.environ)
         env.pop("TMGCN_MERGE_STAGED", None)
         env.pop("TMGCN_MERGE_TT", None)
         if flag == "tiled":
-            env["TMGCN_MERGE_TT"] = "1"         # four output slices per merge pass (fp32 values, b <= 12)
+            env["TMGCN_MERGE_TT"] = "1"         # four output slices per merge pass (fp32 values, b <= 12): the default
+        elif flag == "untiled":
+            env["TMGCN_MERGE_TT"] = "0"         # the per-slice kernels, chosen by row length
         elif flag is not None:
             env["TMGCN_MERGE_STAGED"] = flag
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
         outs[flag] = [ln.split() for ln in r.stdout.strip().splitlines()]
         assert len(outs[flag]) == 8
-    for flag in ("1", "2", "4", None, "tiled"):
+    for flag in ("1", "2", "4", None, "tiled", "untiled"):
         assert outs[flag] == outs["0"], flag
 
 

@@ -81,8 +81,8 @@ def test_band_rejects_non_banded():
     import tmgcn_b200
     with pytest.raises(NotImplementedError):
         tmgcn_b200.Band(torch.ones(5, 5, dtype=torch.float64))
-    with pytest.raises(NotImplementedError):
-        tmgcn_b200.Band(torch.tril(torch.ones(40, 40, dtype=torch.float64)))   # band 40 > 32
+    wide = tmgcn_b200.Band(torch.tril(torch.ones(40, 40, dtype=torch.float64)))   # band 40 > 32: lag blocks
+    assert wide.b == 40 and [(o, sub.b, sub.T) for o, sub in wide.chunks()] == [(0, 32, 40), (32, 8, 8)]
     with pytest.raises(ValueError):
         tmgcn_b200.Band(torch.ones(3, 4))
 

@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(32) merge_rows_staged(const int64_t *__restric
     }
 }
 
-// Time-tiled fill (opt-in: TMGCN_MERGE_TT=1; fp32 values, b <= 12).  TT = 4 consecutive output slices of the
+// Time-tiled fill (default for fp32 values, b <= 12, short rows; TMGCN_MERGE_TT=0 disables).  TT = 4 consecutive output slices of the
 // same 32 rows share B-1 of their B source slices, so ONE merge over the NS = B-1+TT sources feeds all four:
 // a step takes the smallest pending column, every cursor sitting on it hands over its value, and output tt
 // (whose window is slots tt .. tt+B-1) accumulates its own fp64 chain over its slots in ascending slice order
@@ -778,9 +778,11 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
         static int tiled = -1;
         if (tiled < 0) {
             const char *e = getenv("TMGCN_MERGE_TT");
-            tiled = (e && e[0] == '1') ? 1 : 0;
+            tiled = (e && e[0] == '0') ? 0 : 1;          // default on (TMGCN_MERGE_TT=0 selects the per-slice kernels)
         }
-        if (tiled && b <= 12) {
+        // the tiled kernel pays off when a warp's B-1+4 source segments fit its staging pool (sel >= 1 says the
+        // per-slice staged kernel would fit too); forced variants (TMGCN_MERGE_STAGED) bypass it
+        if (tiled && b <= 12 && forced < 0 && sel >= 1 && T_out >= 4) {
             const int pool = (38 * 1024) / 8;                               // entries of {col, val}
             const size_t smem = (size_t)pool * 8;
             const int64_t n_tasks = (int64_t)ceil_div(T_out, 4) * ceil_div(N, (int64_t)32);

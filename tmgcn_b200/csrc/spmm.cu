@@ -137,23 +137,46 @@ __global__ void __launch_bounds__(256, MINB) spmm_rows(const int64_t *__restrict
     }
 }
 
-// Skinny operand (F = 4 floats per row, e.g. the 2C-column factor of the low-rank backward): a row gather is
-// a single 16-byte load, so lanes are spread over the NONZEROS of a row instead of over features.  LPR lanes
-// share a row and a warp takes 32/LPR consecutive rows per iteration, so the dependent chain
-// rowptr -> (col, val) -> gather is paid once per 32/LPR rows (warp-per-row was latency-bound: 20 ms for
-// 1.2 G nonzeros); the rows' nonzeros are contiguous, so the (col, val) loads stay coalesced.  The x slice
-// (N * 16 B) is L2-resident.
-template <int ACT, int LPR>
-__global__ void __launch_bounds__(256, 6) spmm_skinny4(const int64_t *__restrict__ rowptr,
-                                                       const int32_t *__restrict__ col, const float *__restrict__ val,
-                                                       const float *__restrict__ x, float *__restrict__ y,
-                                                       int64_t n_rows, int64_t N) {
+// Skinny operand (W = 4, 6 or 8 floats per row: the 2C-column factor of the low-rank backward for C = 2, 3, 4
+// classes): a row gather is one or two small vector loads, so lanes are spread over the NONZEROS of a row
+// instead of over features.  LPR lanes share a row and a warp takes 32/LPR consecutive rows per iteration, so
+// the dependent chain rowptr -> (col, val) -> gather is paid once per 32/LPR rows (warp-per-row was
+// latency-bound: 20 ms for 1.2 G nonzeros); the rows' nonzeros are contiguous, so the (col, val) loads stay
+// coalesced.  The x slice (N * 4W bytes) is L2-resident.
+template <int W>
+struct SkinnyRow {                       // W floats as W/2 float2 (rows are 8-byte aligned for every even W)
+    float2 v[W / 2];
+};
+template <int W>
+__device__ __forceinline__ SkinnyRow<W> skinny_load(const float *x, int64_t row) {
+    SkinnyRow<W> r;
+    if (W % 4 == 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(x) + row * (W / 4);
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) {
+            const float4 q = __ldg(p + i);
+            r.v[2 * i] = make_float2(q.x, q.y);
+            r.v[2 * i + 1] = make_float2(q.z, q.w);
+        }
+    } else {
+        const float2 *p = reinterpret_cast<const float2 *>(x) + row * (W / 2);
+#pragma unroll
+        for (int i = 0; i < W / 2; ++i) r.v[i] = __ldg(p + i);
+    }
+    return r;
+}
+
+template <int ACT, int LPR, int W>
+__global__ void __launch_bounds__(256, 6) spmm_skinny(const int64_t *__restrict__ rowptr,
+                                                      const int32_t *__restrict__ col, const float *__restrict__ val,
+                                                      const float *__restrict__ x, float *__restrict__ y,
+                                                      int64_t n_rows, int64_t N) {
     constexpr int RPW = 32 / LPR;                      // rows per warp iteration
+    constexpr int UN = W <= 4 ? 4 : 2;                 // passes in flight (register budget)
     const int lane = threadIdx.x & 31;
     const int g = lane / LPR, gl = lane % LPR;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_blk = (n_rows + RPW - 1) / RPW;
-    const float4 *x4 = reinterpret_cast<const float4 *>(x);
     for (int64_t blk = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < n_blk; blk += warps_total) {
         const int64_t row = blk * RPW + g;
         const bool live = row < n_rows;
@@ -163,42 +186,78 @@ __global__ void __launch_bounds__(256, 6) spmm_skinny4(const int64_t *__restrict
             e = rowptr[row + 1];
             xbase = (row / N) * N;
         }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // 4 passes at a time: all (col, val) loads first, then all gathers -- two dependent latencies per
-        // 4*LPR nonzeros of a row instead of two per LPR
-        for (int64_t k = s + gl; k < e; k += 4 * LPR) {
-            int c[4];
-            float v[4];
+        float acc[W];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+        for (int i = 0; i < W; ++i) acc[i] = 0.f;
+        // UN passes at a time: all (col, val) loads first, then all gathers -- two dependent latencies per
+        // UN*LPR nonzeros of a row instead of two per LPR
+        for (int64_t k = s + gl; k < e; k += UN * LPR) {
+            int c[UN];
+            float v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
                 const int64_t kk = k + u * LPR;
                 c[u] = kk < e ? col[kk] : -1;
                 v[u] = kk < e ? val[kk] : 0.f;
             }
-            float4 xv[4];
+            SkinnyRow<W> xv[UN];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                xv[u] = c[u] >= 0 ? __ldg(x4 + xbase + c[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < UN; ++u) {
+                if (c[u] >= 0) {
+                    xv[u] = skinny_load<W>(x, xbase + c[u]);
+                } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                acc.x = fmaf(v[u], xv[u].x, acc.x);
-                acc.y = fmaf(v[u], xv[u].y, acc.y);
-                acc.z = fmaf(v[u], xv[u].z, acc.z);
-                acc.w = fmaf(v[u], xv[u].w, acc.w);
+                    for (int i = 0; i < W / 2; ++i) xv[u].v[i] = make_float2(0.f, 0.f);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+#pragma unroll
+                for (int i = 0; i < W / 2; ++i) {
+                    acc[2 * i] = fmaf(v[u], xv[u].v[i].x, acc[2 * i]);
+                    acc[2 * i + 1] = fmaf(v[u], xv[u].v[i].y, acc[2 * i + 1]);
+                }
         }
 #pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-        }
+        for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < W; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
         if (live && gl == 0) {
-            vact<ACT>(acc);
-            reinterpret_cast<float4 *>(y)[row] = acc;
+#pragma unroll
+            for (int i = 0; i < W / 2; ++i)
+                reinterpret_cast<float2 *>(y)[row * (W / 2) + i] =
+                    make_float2(act_apply<ACT>(acc[2 * i]), act_apply<ACT>(acc[2 * i + 1]));
         }
     }
+}
+
+template <int W>
+static int launch_skinny(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y, int T,
+                         int64_t N, int act, cudaStream_t st) {
+    // One launch per group of slices whose operand (N * 4W B each) fits comfortably in L2: inside a single
+    // grid-stride launch over all T slices the warps drift apart (measured 138 -> 58 Gnnz/s from T = 6 to
+    // T = 32) until several operand slices compete for L2 and the small gathers go to DRAM.
+    const int64_t slice_bytes = N * 4 * W;
+    int64_t per_launch = (int64_t)(l2_bytes() / 3) / (slice_bytes > 0 ? slice_bytes : 1);
+    if (per_launch < 1) per_launch = 1;
+    for (int64_t t0 = 0; t0 < T; t0 += per_launch) {
+        const int64_t rows = (t0 + per_launch < T ? per_launch : T - t0) * N;
+        const int64_t *rp = rowptr + t0 * N;
+        const float *xs = x + t0 * N * W;
+        float *ys = y + t0 * N * W;
+        int64_t blocks = ceil_div(rows, 8 * 4);
+        const int64_t cap = (int64_t)sm_count() * 6 * 8;
+        if (blocks > cap) blocks = cap;
+        switch (act) {
+            case TMGCN_ACT_NONE: spmm_skinny<TMGCN_ACT_NONE, 8, W><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+            case TMGCN_ACT_RELU: spmm_skinny<TMGCN_ACT_RELU, 8, W><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+            case TMGCN_ACT_LEAKY: spmm_skinny<TMGCN_ACT_LEAKY, 8, W><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+            case TMGCN_ACT_SELU: spmm_skinny<TMGCN_ACT_SELU, 8, W><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
+            default: set_error("spmm: unknown activation %d", act); return 1;
+        }
+        if (after_launch("spmm_skinny")) return 1;
+    }
+    return 0;
 }
 
 template <int VEC, int G>
@@ -249,32 +308,9 @@ extern "C" int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const f
     cudaStream_t st = (cudaStream_t)stream;
     const bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     const bool a8 = ((uintptr_t)x % 8 == 0) && ((uintptr_t)y % 8 == 0);
-    if (F == 4 && a16) {
-        // One launch per group of slices whose operand (N * 16 B each) fits comfortably in L2: inside a single
-        // grid-stride launch over all T slices the warps drift apart (measured 138 -> 58 Gnnz/s from T = 6 to
-        // T = 32) until several operand slices compete for L2 and the 16-byte gathers go to DRAM.
-        const int64_t slice_bytes = N * 16;
-        int64_t per_launch = (int64_t)(l2_bytes() / 3) / (slice_bytes > 0 ? slice_bytes : 1);
-        if (per_launch < 1) per_launch = 1;
-        for (int64_t t0 = 0; t0 < T; t0 += per_launch) {
-            const int64_t rows = (t0 + per_launch < T ? per_launch : T - t0) * N;
-            const int64_t *rp = rowptr + t0 * N;
-            const float *xs = x + t0 * N * 4;
-            float *ys = y + t0 * N * 4;
-            int64_t blocks = ceil_div(rows, 8 * 4);
-            const int64_t cap = (int64_t)sm_count() * 6 * 8;
-            if (blocks > cap) blocks = cap;
-            switch (act) {
-                case TMGCN_ACT_NONE: spmm_skinny4<TMGCN_ACT_NONE, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
-                case TMGCN_ACT_RELU: spmm_skinny4<TMGCN_ACT_RELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
-                case TMGCN_ACT_LEAKY: spmm_skinny4<TMGCN_ACT_LEAKY, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
-                case TMGCN_ACT_SELU: spmm_skinny4<TMGCN_ACT_SELU, 8><<<(unsigned)blocks, 256, 0, st>>>(rp, col, val, xs, ys, rows, N); break;
-                default: set_error("spmm: unknown activation %d", act); return 1;
-            }
-            if (after_launch("spmm_skinny4")) return 1;
-        }
-        return 0;
-    }
+    if (F == 4 && a16) return launch_skinny<4>(rowptr, col, val, x, y, T, N, act, st);
+    if (F == 6 && a8) return launch_skinny<6>(rowptr, col, val, x, y, T, N, act, st);
+    if (F == 8 && a16) return launch_skinny<8>(rowptr, col, val, x, y, T, N, act, st);
     if (F % 4 == 0 && a16) return launch_spmm_g<4>(rowptr, col, val, x, y, n_rows, N, F, act, st);
     if (F % 2 == 0 && a8) return launch_spmm_g<2>(rowptr, col, val, x, y, n_rows, N, F, act, st);
     return launch_spmm_g<1>(rowptr, col, val, x, y, n_rows, N, F, act, st);

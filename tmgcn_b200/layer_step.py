@@ -56,6 +56,10 @@ class LayerStep:
                 At.rowptr.device).multi_processor_count))
         self.boundary_ctas = boundary_ctas
         self.At, self.AtT = At, At.transpose()
+        if band.b > Band.MAX_KERNEL_BAND:
+            raise NotImplementedError(f"LayerStep: band width {band.b} > {Band.MAX_KERNEL_BAND} (use the autograd ops)")
+        if C > ops.MAX_FUSED_CLASSES:
+            raise NotImplementedError(f"LayerStep: {C} classes > {ops.MAX_FUSED_CLASSES} (use the autograd ops)")
         self.band, self.plan = band, plan
         self.t0, self.t1, self.halo = t0, (band.T if t1 is None else t1), halo
         self.T, self.N = At.T, At.N

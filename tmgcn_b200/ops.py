@@ -135,6 +135,20 @@ class SliceCSR:
             val = torch.cat(vs)
         return SliceCSR.from_coo(idx, val, len(slices), N, dtype)
 
+    def time_window(self, start: int, end: int) -> "SliceCSR":
+        """slices [start, end) re-based to 0 (ref: func_create_sparse, read_data.py:174-183)"""
+        N = self.N
+        lo, hi = int(self.rowptr[start * N].item()), int(self.rowptr[end * N].item())
+        return SliceCSR(end - start, N, (self.rowptr[start * N:end * N + 1] - lo).contiguous(),
+                        self.col[lo:hi].contiguous(), self.val[lo:hi].contiguous())
+
+    def concat(self, other: "SliceCSR") -> "SliceCSR":
+        """[self | other] along time"""
+        assert self.N == other.N and self.val.dtype == other.val.dtype
+        rowptr = torch.cat([self.rowptr[:-1], other.rowptr + self.rowptr[-1]])
+        return SliceCSR(self.T + other.T, self.N, rowptr, torch.cat([self.col, other.col]),
+                        torch.cat([self.val, other.val]))
+
     def row_ids(self) -> torch.Tensor:
         counts = self.rowptr[1:] - self.rowptr[:-1]
         return torch.repeat_interleave(torch.arange(self.T * self.N, device=self.rowptr.device), counts)
@@ -174,7 +188,9 @@ class Band:
     """Banded lower-triangular M (ref: SBM_our.py:88-96, read_data.py:56-62):
     w[t, i] = M[t, t-i].  `rows` selects the output slices a rank owns."""
 
-    def __init__(self, M: torch.Tensor, max_b: int = 32):
+    MAX_KERNEL_BAND = 32      # widest band one kernel launch handles (register ring / cursor count)
+
+    def __init__(self, M: torch.Tensor):
         M = torch.as_tensor(M).detach().to("cpu", torch.float64)
         if M.dim() != 2 or M.shape[0] != M.shape[1]:
             raise ValueError("M must be a square matrix")
@@ -183,13 +199,30 @@ class Band:
         T = M.shape[0]
         nz = torch.nonzero(M)
         b = int((nz[:, 0] - nz[:, 1]).max()) + 1 if nz.numel() else 1
-        if b > max_b:
-            raise NotImplementedError(f"band width {b} > {max_b} unsupported")
         w = torch.zeros(T, b, dtype=torch.float64)
         for i in range(b):
             w[i:, i] = torch.diagonal(M, -i)
         self.T, self.b, self.w = T, b, w
         self._dev = {}
+
+    @classmethod
+    def _from_weights(cls, w: torch.Tensor) -> "Band":
+        self = cls.__new__(cls)
+        self.T, self.b, self.w, self._dev = int(w.shape[0]), int(w.shape[1]), w.contiguous(), {}
+        return self
+
+    def chunks(self):
+        """A band wider than one kernel handles, as lag blocks: [(o, sub)] with sub.w[t', i] = w[t' + o, o + i],
+        so that M x_3 X = sum over blocks of (sub x_3 X[:T-o]) placed at output slices [o, T)."""
+        out = []
+        for o in range(0, self.b, self.MAX_KERNEL_BAND):
+            if o < self.T:
+                out.append((o, Band._from_weights(self.w[o:, o:min(self.b, o + self.MAX_KERNEL_BAND)])))
+        return out
+
+    def _whole_only(self, t0, t1, halo, what):
+        if self.b > self.MAX_KERNEL_BAND and not (t0 == 0 and t1 == self.T and halo == 0):
+            raise NotImplementedError(f"{what}: bands wider than {self.MAX_KERNEL_BAND} are only supported unsharded")
 
     def device_weights(self, t0: int, t1: int, dtype) -> torch.Tensor:
         key = (t0, t1, dtype, torch.cuda.current_device())
@@ -206,6 +239,19 @@ def mtransform_sparse(csr: SliceCSR, band: Band, t0: int = 0, t1: Optional[int] 
     T_out = t1 - t0
     if csr.T != T_out + halo:
         raise ValueError(f"input has {csr.T} slices, expected halo + T_out = {halo + T_out}")
+    if band.b > Band.MAX_KERNEL_BAND:
+        # wide band: one merge per block of 32 lags on the time-shifted input, partial tensors added by the
+        # sorted 2-way row merge (same union pattern and order; the fp64 sums are grouped per block)
+        band._whole_only(t0, t1, halo, "mtransform_sparse")
+        out = None
+        for o, sub in band.chunks():
+            part = mtransform_sparse(csr.time_window(0, csr.T - o), sub)
+            if out is None:
+                out = part
+            else:
+                tail = csr_axpby(out.time_window(o, out.T), part, 1.0, 1.0)
+                out = out.time_window(0, o).concat(tail)
+        return out
     f64 = csr.val.dtype == torch.float64
     w = band.device_weights(t0, t1, torch.float64)
     N = csr.N
@@ -223,6 +269,24 @@ def mtransform_sparse(csr: SliceCSR, band: Band, t0: int = 0, t1: Optional[int] 
     return SliceCSR(T_out, N, rowptr, col, val)
 
 
+def csr_axpby(A: SliceCSR, B: SliceCSR, alpha: float, beta: float) -> SliceCSR:
+    """alpha*A + beta*B (sorted 2-way row merge; union pattern, explicit zeros kept)."""
+    assert A.T == B.T and A.N == B.N and A.val.dtype == B.val.dtype
+    lib = _lib.load()
+    n_rows = A.T * A.N
+    dev = A.rowptr.device
+    counts = torch.empty(n_rows, dtype=torch.int64, device=dev)
+    _lib.check(lib.tmgcn_csr_axpby_plan(_p(A.rowptr), _p(A.col), _p(B.rowptr), _p(B.col), n_rows, _p(counts), _stream()))
+    rowptr = exclusive_scan(counts)
+    nnz = int(rowptr[-1].item())
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    val = torch.empty(nnz, dtype=A.val.dtype, device=dev)
+    _lib.check(lib.tmgcn_csr_axpby_run(_p(A.rowptr), _p(A.col), _p(A.val), _p(B.rowptr), _p(B.col), _p(B.val),
+                                       float(alpha), float(beta), n_rows, _p(rowptr), _p(col), _p(val),
+                                       1 if A.val.dtype == torch.float64 else 0, _stream()))
+    return SliceCSR(A.T, A.N, rowptr, col, val)
+
+
 # --------------------------------------------------------------------------
 # raw (non-autograd) kernels
 # --------------------------------------------------------------------------
@@ -232,6 +296,16 @@ def stencil_fwd(x: torch.Tensor, band: Band, t0: int = 0, t1: Optional[int] = No
     T_out = t1 - t0
     x = _f32(x)
     assert x.shape[0] == T_out + halo, "x must hold halo + T_out slices"
+    if band.b > Band.MAX_KERNEL_BAND:            # wide band: one launch per block of 32 lags, partial sums added
+        band._whole_only(t0, t1, halo, "mtransform_dense")
+        out = None
+        for o, sub in band.chunks():
+            part = stencil_fwd(x[: x.shape[0] - o], sub)
+            if out is None:
+                out = part
+            else:
+                out[o:].add_(part)
+        return out
     NF = x[0].numel() if x.shape[0] else 0
     out = torch.empty((T_out,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
     w = band.device_weights(t0, t1, torch.float32)
@@ -245,6 +319,16 @@ def stencil_bwd(g: torch.Tensor, band: Band, t0: int = 0, t1: Optional[int] = No
     T_out = t1 - t0
     g = _f32(g)
     assert g.shape[0] == T_out
+    if band.b > Band.MAX_KERNEL_BAND:
+        band._whole_only(t0, t1, halo, "mtransform_dense")
+        out = None
+        for o, sub in band.chunks():
+            part = stencil_bwd(g[o:], sub)                 # gradient w.r.t. x[:T-o]
+            if out is None:
+                out = part
+            else:
+                out[: g.shape[0] - o].add_(part)
+        return out
     NF = g[0].numel() if g.shape[0] else 0
     out = torch.empty((T_out + halo,) + tuple(g.shape[1:]), dtype=torch.float32, device=g.device)
     w = band.device_weights(t0, t1, torch.float32)
@@ -609,6 +693,9 @@ def mtransform_dense_inv(z, band: Band):
     """inv(M) x_3 Z (ref: ehf:223-224), differentiable; M banded lower triangular with a nonzero diagonal."""
     if bool((band.w[:, 0] == 0).any()):
         raise ValueError("M has a zero on its diagonal: not invertible")
+    if band.b > Band.MAX_KERNEL_BAND:
+        raise NotImplementedError(f"inv(M) x_3 Z: the substitution kernel keeps the last b-1 outputs in registers; "
+                                  f"b = {band.b} > {Band.MAX_KERNEL_BAND} is not supported")
     return _Solve.apply(z, band)
 
 

@@ -26,22 +26,7 @@ def _to_coo(C: SliceCSR) -> torch.Tensor:
     return torch.sparse_coo_tensor(idx, val, (C.T, C.N, C.N), is_coalesced=True)
 
 
-def csr_axpby(A: SliceCSR, B: SliceCSR, alpha: float, beta: float) -> SliceCSR:
-    """alpha*A + beta*B (sorted 2-way row merge; union pattern, explicit zeros kept)."""
-    assert A.T == B.T and A.N == B.N and A.val.dtype == B.val.dtype
-    lib = _lib.load()
-    n_rows = A.T * A.N
-    dev = A.rowptr.device
-    counts = torch.empty(n_rows, dtype=torch.int64, device=dev)
-    _lib.check(lib.tmgcn_csr_axpby_plan(_p(A.rowptr), _p(A.col), _p(B.rowptr), _p(B.col), n_rows, _p(counts), _stream()))
-    rowptr = ops.exclusive_scan(counts)
-    nnz = int(rowptr[-1].item())
-    col = torch.empty(nnz, dtype=torch.int32, device=dev)
-    val = torch.empty(nnz, dtype=A.val.dtype, device=dev)
-    _lib.check(lib.tmgcn_csr_axpby_run(_p(A.rowptr), _p(A.col), _p(A.val), _p(B.rowptr), _p(B.col), _p(B.val),
-                                       float(alpha), float(beta), n_rows, _p(rowptr), _p(col), _p(val),
-                                       1 if A.val.dtype == torch.float64 else 0, _stream()))
-    return SliceCSR(A.T, A.N, rowptr, col, val)
+csr_axpby = ops.csr_axpby
 
 
 def make_symmetric_csr(A: SliceCSR) -> SliceCSR:
@@ -75,10 +60,7 @@ def laplacian_transformation_csr(B: SliceCSR) -> SliceCSR:
 
 def create_sparse_csr(A: SliceCSR, start: int, end: int) -> SliceCSR:
     """time window [start, end) re-based to 0 (ref: read_data.py:174-183)."""
-    N = A.N
-    lo, hi = int(A.rowptr[start * N].item()), int(A.rowptr[end * N].item())
-    return SliceCSR(end - start, N, (A.rowptr[start * N:end * N + 1] - lo).contiguous(), A.col[lo:hi].contiguous(),
-                    A.val[lo:hi].contiguous())
+    return A.time_window(start, end)
 
 
 # ---- the reference's call surface (sparse COO in, sparse COO out) -------------------------------

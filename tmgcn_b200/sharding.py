@@ -276,11 +276,18 @@ class PeerHalo:
 
 def _device_local_solve(src, dst, halo, T, h, n, ld, ld_halo, w, b, transposed):
     """one column chunk of the banded substitution on the device (C ABI: tmgcn_mtransform_dense_solve_part)"""
+    import ctypes
     from . import _lib
     from .ops import _p, _stream
+
+    def view_ptr(v, row_stride):      # a column window of a row-major matrix: rows `row_stride` floats apart
+        assert v.is_cuda and v.dtype == torch.float32 and v.stride(-1) == 1 and (v.shape[0] <= 1 or v.stride(0) == row_stride)
+        return ctypes.c_void_p(v.data_ptr())
     lib = _lib.load()
-    _lib.check(lib.tmgcn_mtransform_dense_solve_part(_p(src), _p(dst), _p(halo) if h > 0 else None, T, h, n, ld,
-                                                     ld_halo, _p(w), b, 1 if transposed else 0, _stream()))
+    _lib.check(lib.tmgcn_mtransform_dense_solve_part(view_ptr(src, ld), view_ptr(dst, ld),
+                                                     view_ptr(halo, ld_halo) if h > 0 else None, T, h, n, ld,
+                                                     ld_halo, _p(w, torch.float32), b, 1 if transposed else 0,
+                                                     _stream()))
 
 
 def solve_pipelined(z: torch.Tensor, band, t0: int, t1: int, rank: int, world: int, transposed: bool = False,
