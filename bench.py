@@ -125,6 +125,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tf32_peak():
+    """TF32 tensor-core peak measured on this pool's B200 by scripts/measure_tf32_peak.py (cuBLAS, 8192^3),
+    committed as profiles/r02_tf32_peak.json -- MEASURED_PEAKS.json holds only the bf16 figure."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_tf32_peak.json")))
+        return float(d["tf32_tflops"]), float(d["tf32_tflops_sustained"])
+    except Exception:
+        return None, None
+
+
 def measured_traffic(wl, T_own, world):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very config
     (profiles/r02_traffic.json, else r01), or None when the config differs."""
@@ -470,6 +480,8 @@ def run_workload(wl, ctx, steps, warmup, full):
             copy_stream.synchronize()                   # the step's results are on the host
         return dH
 
+    host_ms = [0.0]
+
     def timed(K, e2e, stage_times=None):
         events = []
 
@@ -483,12 +495,14 @@ def run_workload(wl, ctx, steps, warmup, full):
         if flush:
             # small workload: rewrite a buffer larger than L2 before every step; each step is timed on its own
             # pair of events so the flush stays outside the timed region
-            ms = 0.0
+            ms, host = 0.0, 0.0
             for _ in range(K):
                 ctx.flush_l2()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
+                h0 = time.perf_counter()
                 one_step(e2e)
+                host += time.perf_counter() - h0
                 e.record()
                 torch.cuda.synchronize()
                 ms += s.elapsed_time(e)
@@ -496,11 +510,14 @@ def run_workload(wl, ctx, steps, warmup, full):
         else:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
+            h0 = time.perf_counter()
             for _ in range(K):
                 one_step(e2e)
+            host = time.perf_counter() - h0          # how long the host needed to ENQUEUE the K steps
             e.record()
             ctx.barrier()
             ms = s.elapsed_time(e)
+        host_ms[0] = host * 1e3 / K
         step.hook = None
         if stage_times is not None:
             per_step = {}
@@ -521,6 +538,7 @@ def run_workload(wl, ctx, steps, warmup, full):
     sampler = ClockSampler(ctx.local) if (rank == 0 and full) else None
     stage_times = {}
     ms, launches = timed(steps, False, stage_times)
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
     ms_e2e = None
     if full:
@@ -565,7 +583,7 @@ def run_workload(wl, ctx, steps, warmup, full):
         "scaling": wl["scaling"], "T_total": T_total, "ms_per_step": sec * 1e3, "value": slice_edges / sec,
         "steps": steps, "warmup": W_, "slice_edges_per_step": slice_edges, "input_edges_per_step": nnz_in_total,
         "slice_edges_per_rank": per_rank_nnz, "gpu_launches": launches, "halo_mode": halo_mode,
-        "backward_mode": step.bwd_mode, "clocks": clocks,
+        "backward_mode": step.bwd_mode, "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms,
         "stages": stage_table(stages_all[0], alg), "stages_ms_per_rank": stages_all if world > 1 else None,
         "alg": alg, "layer_algorithmic_bytes": sum(alg.values()),
         "E": E, "F": F, "C": C,
@@ -600,6 +618,65 @@ def run_workload(wl, ctx, steps, warmup, full):
     return res
 
 
+def module_fresh_input_leg(args, ctx, with_cpu=True, calls=5):
+    """The reference's OTHER call form, `gcn(At, X, edges)` with fresh inputs (ehf:212-215: every evaluation,
+    experiment_bitcoin_our.py:134,145), end to end through the module API with HOST inputs: a new Python list of
+    CPU sparse slices, a CPU fp64 X and CPU edges go in, CPU logits come out, every call (list -> device CSR,
+    M-transform of X, facewise SpMM, GEMM, readout; no_grad as in the reference's evaluation).  Config:
+    configs[0] shape with the experiment's own widths (N = 5 881, T = 95, b = 20, F 2 -> 6 -> 2, 1 layer,
+    experiment_bitcoin_our.py:109).  The CPU arm runs the oracle port of the same call on the same data."""
+    import oracle
+    import tmgcn_b200 as tg
+    from tmgcn_b200 import synth
+    N, T, m, b, F0, F1, C = 5_881, 95, 2_580, 20, 2, 6, 2
+    idx, val = synth.synth_coo(N, T, m, 0.9, seed=SEED, device="cpu")
+    M = oracle.create_matrix_M(T, b)
+    ai, av = oracle.func_MProduct(idx.numpy(), val.numpy(), (T, N, N), M.numpy())
+    nnz = int(ai.shape[1])
+    At = [a.coalesce() for a in oracle.split_slices(ai, av, T, N)]
+    g = torch.Generator().manual_seed(SEED)
+    X = torch.rand(T, N, F0, generator=g, dtype=torch.float64)
+    E = m * T // 8
+    pick = torch.sort(torch.randint(0, nnz, (E,), generator=g)).values
+    edges = torch.from_numpy(ai[:, pick.numpy()])
+    torch.manual_seed(SEED)
+    gcn = tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[F1, C], condensed_W=True, use_Minv=False)
+    h2d = nnz * (3 * 8 + 8) + X.numel() * 8 + edges.numel() * 8
+    d2h = E * C * 4
+    with torch.no_grad():
+        for _ in range(2):
+            out = gcn(list(At), X, edges).cpu()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            out = gcn(list(At), X, edges).cpu()          # a NEW list object: the module's CSR cache cannot hit
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / calls
+    res = {"what": "module call gcn(At, X, edges) with fresh HOST inputs (ehf:212-215), no_grad, logits back on the "
+                   "host; wall clock per call including list -> CSR conversion and all copies",
+           "config": f"configs[0] shape, reference widths: N={N}, T={T}, b={b}, F {F0}->{F1}->{C}, 1 layer "
+                     f"(EmbeddingGCN), E={E}, {nnz} slice-edges",
+           "value": nnz / sec, "unit": "slice-edges/s", "ms_per_call": sec * 1e3,
+           "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h}
+    if with_cpu:
+        ref = oracle.OracleGCN(At, X, edges, M, gcn.W.detach().cpu(), gcn.U.detach().cpu(), as_reference=True)
+        with torch.no_grad():
+            ref(At, X, edges)
+            t0 = time.perf_counter()
+            for _ in range(calls):
+                out_r = ref(At, X, edges)
+            sec_r = (time.perf_counter() - t0) / calls
+        err = ((out.double() - out_r.double()).abs().max() / out_r.double().abs().max()).item()
+        res["cpu"] = {"value": nnz / sec_r, "unit": "slice-edges/s", "ms_per_call": sec_r * 1e3,
+                      "cores": len(os.sched_getaffinity(0)), "kind": "port"}
+        res["ratio"] = sec_r / sec
+        res["rel_err_vs_cpu_port"] = err
+    del gcn
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
 def roofline_of(res, stages_key, dom, peak, peak_src, traffic=None):
     st = res[stages_key] if stages_key == "stages" else res["dense"]["stages"]
     algb = res["alg"] if stages_key == "stages" else res["dense"]["alg"]
@@ -613,7 +690,7 @@ def slim(res, peak):
     """the part of a workload's measurements that goes into the strong_scaling / same_config sub-objects"""
     out = {k: res[k] for k in ("config", "scaling", "T_total", "ms_per_step", "value", "steps", "warmup",
                                "slice_edges_per_step", "slice_edges_per_rank", "halo_mode", "backward_mode",
-                               "stages", "stages_ms_per_rank")}
+                               "host_enqueue_ms_per_step", "stages", "stages_ms_per_rank")}
     out["layer_hbm_frac"] = res["layer_algorithmic_bytes"] / (res["ms_per_step"] * 1e-3) / 1e9 / peak
     if "dense" in res:
         out["dense"] = {k: res["dense"][k] for k in ("ms_per_step", "value", "stages", "stages_ms_per_rank")}
@@ -641,7 +718,7 @@ def run_ours(args):
     wl = resolve_workload(args)
     res = run_workload(wl, ctx, args.steps, args.warmup, full=True)
 
-    strong, same_cfg = {}, None
+    strong, same_cfg, fresh = {}, None, None
     if extras:
         k_x = max(3, min(args.steps, 10))
         for name in ("c5cut", "c4"):
@@ -664,6 +741,10 @@ def run_ours(args):
                                         "host); the CPU arm is one timed step without warm-up")
             except Exception as ex:
                 same_cfg = {"error": f"{type(ex).__name__}: {ex}"}
+            try:
+                fresh = module_fresh_input_leg(args, ctx, with_cpu=not args.no_cpu_baseline)
+            except Exception as ex:
+                fresh = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
         dom = "spmm_fwd"
@@ -688,6 +769,7 @@ def run_ours(args):
             "layer_hbm_frac": res["layer_algorithmic_bytes"] / (res["ms_per_step"] * 1e-3) / 1e9 / peak,
             "layer_algorithmic_bytes": res["layer_algorithmic_bytes"],
             "stages": res["stages"], "stages_ms_per_rank": res["stages_ms_per_rank"],
+            "host_enqueue_ms_per_step": res["host_enqueue_ms_per_step"],
         }
         if "dense" in res:
             d = res["dense"]
@@ -698,6 +780,19 @@ def run_ours(args):
                              "layer_hbm_frac": d["layer_algorithmic_bytes"] / (d["ms_per_step"] * 1e-3) / 1e9 / peak,
                              "roofline": roofline_of(res, "dense", "spmm_bwd", peak, peak_src)}
             line["dense"]["roofline"]["kernel"] = "spmm_rows on the transposed CSR (backward SpMM)"
+        burst, sustained = tf32_peak()
+        g_ms = res["stages"].get("gemm_fwd", {}).get("ms")
+        if burst and g_ms:
+            rows = res["T_own"] * wl["nodes"] if world == 1 else None
+            if rows:
+                useful = 2.0 * rows * wl["feat"] * wl["feat"] / (g_ms * 1e-3) / 1e12
+                line["gemm_tensor_pipe"] = {
+                    "kernel": "gemm_tf32x3_kernel (tcgen05.mma kind::tf32, 3 MMAs per useful product)",
+                    "useful_tflops": useful, "executed_tflops": 3.0 * useful, "tf32_peak_burst": burst,
+                    "tf32_peak_sustained": sustained, "executed_frac_of_sustained_peak": 3.0 * useful / sustained,
+                    "executed_frac_of_burst_peak": 3.0 * useful / burst,
+                    "note": "the kernel is HBM-bound (AI = 32 flop/B): see stages.gemm_fwd GB/s; peaks from "
+                            "profiles/r02_tf32_peak.json (cuBLAS TF32 8192^3 on this pool's B200)"}
         if "mtransform_sparse" in res:
             ms_ = res["mtransform_sparse"]
             ms_["hbm_frac"] = ms_["GB/s"] / peak
@@ -709,6 +804,8 @@ def run_ours(args):
         if same_cfg is not None:
             line["same_config"] = same_cfg
             line["extra"] = {"same_config_ratio": same_cfg.get("ratio")}
+        if fresh is not None:
+            line["e2e_fresh_inputs"] = fresh
         if world == 1 and not args.no_cpu_baseline:
             try:
                 N, T, m, whole = cpu_sample_shape(args, wl)

@@ -122,9 +122,11 @@ int tmgcn_mtransform_dense_fwd_split(const float *x_halo, const float *x_own, fl
                                      int64_t NF, const float *band_w, int b, int max_ctas, void *stream);
 /* same, but only input slices s in [s_begin, s_end) of g_in are written (the others are left untouched):
  * lets a rank produce the `halo` slices it owes its predecessor first (and put them on the wire) and the
- * rest later, in place, without a staging copy. */
+ * rest later, in place, without a staging copy.  Slices s >= acc_begin are ACCUMULATED into (g_in[s] += ...):
+ * the partial sums the successor rank owes this rank's last slices are received straight into g_in while
+ * the backward SpMM runs, and the stencil adds its own contribution on top (acc_begin < 0: overwrite all). */
 int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
-                                     const float *band_w, int b, int s_begin, int s_end, void *stream);
+                                     const float *band_w, int b, int s_begin, int s_end, int acc_begin, void *stream);
 
 /* inverse transform  Y = inv(M) x_3 Z  (ref: Minv = inv(M), ehf:183-184; applied at ehf:223-224, 331-332,
  * 338-341): inv(M) of a banded M is dense, so it is applied as the banded substitution M x_3 Y = Z marching
@@ -148,6 +150,10 @@ int tmgcn_mtransform_dense_solve_part(const float *src, float *dst, const float 
  * The backward (dX_t = A~_t^T . dY_t) is the same call on the transposed CSR. */
 int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y, int T,
                    int64_t N, int F, int act, void *stream);
+/* same, with the number of stored entries the launch covers (rowptr[T*N] - rowptr[0]; -1 = unknown): graphs with
+ * short rows (fewer than 8 entries per row on average) take a software-pipelined kernel. */
+int tmgcn_spmm_fwd_hint(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y, int T,
+                        int64_t N, int F, int act, int64_t nnz, void *stream);
 
 /* ---- (c) feature GEMM  Y = act(P . W) --------------------------------------
  * ref: t.matmul(AtXt, W), ehf:222 / 330 / 344 / 486-489; nonlinearity ehf:332-335.

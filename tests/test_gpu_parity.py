@@ -249,11 +249,18 @@ def test_stencil_fwd_bwd(tg, T, b, NF, norm):
     part = torch.full_like(g_hi, float("nan"))
     hb = min(band.b - 1, T - cut)
     _lib.check(lib.tmgcn_mtransform_dense_bwd_range(ops._p(Gh), ops._p(part), hb, halo, NF, ops._p(w), band.b, 0, halo,
-                                                    ops._stream()))
+                                                    -1, ops._stream()))
     assert torch.equal(part[:halo], g_hi[:halo]) and bool(torch.isnan(part[halo:]).all())
     _lib.check(lib.tmgcn_mtransform_dense_bwd_range(ops._p(Gh), ops._p(part), T - cut, halo, NF, ops._p(w), band.b, halo,
-                                                    halo + T - cut, ops._stream()))
+                                                    halo + T - cut, -1, ops._stream()))
     assert torch.equal(part, g_hi)
+    # accumulate form: the last slices already hold what a successor rank sent; the stencil adds on top
+    acc0 = halo + (T - cut) - min(2, T - cut)
+    seeded = torch.zeros_like(g_hi)
+    seeded[acc0:] = 0.25
+    _lib.check(lib.tmgcn_mtransform_dense_bwd_range(ops._p(Gh), ops._p(seeded), T - cut, halo, NF, ops._p(w), band.b, 0,
+                                                    halo + T - cut, acc0, ops._stream()))
+    assert torch.equal(seeded[:acc0], g_hi[:acc0]) and torch.equal(seeded[acc0:], g_hi[acc0:] + 0.25)
 
 
 # --------------------------------------------------------------------------
@@ -279,6 +286,31 @@ def test_spmm_vs_oracle(tg, F):
     ref_t = oracle.compute_AX([a.t().coalesce() for a in A], X)
     out_t = ops.spmm_raw(csr.transpose(), X.float().cuda())
     assert relerr(out_t, ref_t) <= TOL_OUT
+
+
+@pytest.mark.parametrize("F,act", [(128, "none"), (64, "relu"), (96, "selu"), (256, "none")])
+def test_spmm_short_rows(tg, F, act):
+    """graphs with fewer than 8 stored entries per row (the C1-C4 shapes) take the software-pipelined kernel:
+    ragged rows (empty ones, one 70-entry hub) against the oracle, forward and transposed."""
+    from tmgcn_b200 import ops
+    T, N = 5, 900
+    g = torch.Generator().manual_seed(F)
+    nnz = 2600
+    idx = torch.stack([torch.randint(0, T, (nnz,), generator=g), torch.randint(0, N, (nnz,), generator=g),
+                       torch.randint(0, N, (nnz,), generator=g)])
+    idx[1, :300] = torch.randint(0, 40, (300,), generator=g)       # leaves many rows empty
+    hub = torch.stack([torch.full((70,), 2), torch.full((70,), 11), torch.arange(0, 140, 2)])
+    idx = torch.cat([idx, hub], 1)
+    C = torch.sparse_coo_tensor(idx, torch.rand(idx.shape[1], dtype=torch.float64, generator=g) - 0.3, (T, N, N)).coalesce()
+    assert C._nnz() < 8 * T * N
+    A = oracle.split_slices(C._indices().numpy(), C._values().numpy(), T, N)
+    X = torch.rand(T, N, F, generator=g, dtype=torch.float64) - 0.5
+    ref = oracle.nonlin(act)(oracle.compute_AX(A, X).double())
+    csr = tg.SliceCSR.from_coo(C._indices(), C._values(), T, N)
+    out = ops.spmm_raw(csr, X.float().cuda(), tg.ops.ACT[act])
+    assert relerr(out, ref) <= TOL_OUT
+    ref_t = oracle.compute_AX([a.t().coalesce() for a in A], X)
+    assert relerr(ops.spmm_raw(csr.transpose(), X.float().cuda()), ref_t) <= TOL_OUT
 
 
 @pytest.mark.parametrize("act", ["relu", "leaky", "selu"])

@@ -66,7 +66,8 @@ template <int B, int V, bool REVERSE>
 __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ src_halo,
                                                       const float *__restrict__ src, float *__restrict__ dst,
                                                       int T_out, int halo, int64_t n_vec,
-                                                      const float *__restrict__ band_w, int b, int s_begin, int s_end) {
+                                                      const float *__restrict__ band_w, int b, int s_begin, int s_end,
+                                                      int acc_begin) {
     using VT = typename Vec<V>::T;
     constexpr int C = STENCIL_C, R = ring_size(B);
     extern __shared__ float sw[];
@@ -125,7 +126,12 @@ __global__ void __launch_bounds__(256) stencil_kernel(const float *__restrict__ 
 #pragma unroll
                             for (int i = 0; i < B; ++i)
                                 fma_v(acc, sw[(t0 + i + B) * B + i], ring[(q + k - i + 2 * R) % R]);
-                            if (s >= s_begin && s < s_end) st_v(out + (int64_t)s * n_vec, acc);
+                            if (s >= s_begin && s < s_end) {
+                                // slices >= acc_begin already hold what the successor rank owes them (received
+                                // straight into this tensor): add instead of overwrite
+                                if (s >= acc_begin) fma_v(acc, 1.f, ld_v(out + (int64_t)s * n_vec));
+                                st_v(out + (int64_t)s * n_vec, acc);
+                            }
                         }
                     }
                 }
@@ -219,7 +225,8 @@ static int solve_entry(const float *z, float *y, const float *halo, int T, int h
 
 template <int B, int V, bool REVERSE>
 static int launch_stencil(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
-                          const float *band_w, int b, int s_begin, int s_end, int max_ctas, cudaStream_t st) {
+                          const float *band_w, int b, int s_begin, int s_end, int max_ctas, int acc_begin,
+                          cudaStream_t st) {
     const int64_t n_vec = NF / V;
     const size_t smem = (size_t)(T_out + 2 * B) * B * sizeof(float);
     TMGCN_REQUIRE(smem <= 200 * 1024, "mtransform_dense: T_out=%d too large for the weight table (b=%d)", T_out, b);
@@ -231,17 +238,19 @@ static int launch_stencil(const float *src_halo, const float *src, float *dst, i
     const int threads = max_ctas > 0 ? 128 : 256;
     int64_t grid = ceil_div(n_vec, threads);
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    kern<<<(unsigned)grid, threads, smem, st>>>(src_halo, src, dst, T_out, halo, n_vec, band_w, b, s_begin, s_end);
+    kern<<<(unsigned)grid, threads, smem, st>>>(src_halo, src, dst, T_out, halo, n_vec, band_w, b, s_begin, s_end,
+                                                acc_begin);
     return after_launch(REVERSE ? "stencil_bwd" : "stencil_fwd");
 }
 
 template <int V, bool REVERSE>
 static int dispatch_b(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
-                      const float *band_w, int b, int s_begin, int s_end, int max_ctas, cudaStream_t st) {
+                      const float *band_w, int b, int s_begin, int s_end, int max_ctas, int acc_begin,
+                      cudaStream_t st) {
 #define TMGCN_CASE(BB)                                                                                             \
     if (b <= BB)                                                                                                   \
         return launch_stencil<BB, V, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end,     \
-                                              max_ctas, st);
+                                              max_ctas, acc_begin, st);
     TMGCN_CASE(1)
     TMGCN_CASE(2)
     TMGCN_CASE(4)
@@ -260,7 +269,8 @@ static int dispatch_b(const float *src_halo, const float *src, float *dst, int T
 
 template <bool REVERSE>
 static int stencil_entry(const float *src_halo, const float *src, float *dst, int T_out, int halo, int64_t NF,
-                         const float *band_w, int b, int s_begin, int s_end, void *stream, int max_ctas = 0) {
+                         const float *band_w, int b, int s_begin, int s_end, void *stream, int max_ctas = 0,
+                         int acc_begin = 0x7fffffff) {
     TMGCN_REQUIRE(T_out >= 0 && NF >= 0 && halo >= 0, "mtransform_dense: negative size");
     TMGCN_REQUIRE(b >= 1 && b <= 32, "mtransform_dense: band width b=%d outside [1, 32]", b);
     TMGCN_REQUIRE(halo <= b - 1, "mtransform_dense: halo=%d exceeds b-1=%d", halo, b - 1);
@@ -270,8 +280,10 @@ static int stencil_entry(const float *src_halo, const float *src, float *dst, in
     const bool vec4 = (NF % 4 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) &&
                       ((uintptr_t)src_halo % 16 == 0);
     if (vec4)
-        return dispatch_b<4, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, max_ctas, st);
-    return dispatch_b<1, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, max_ctas, st);
+        return dispatch_b<4, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, max_ctas,
+                                      acc_begin, st);
+    return dispatch_b<1, REVERSE>(src_halo, src, dst, T_out, halo, NF, band_w, b, s_begin, s_end, max_ctas, acc_begin,
+                                  st);
 }
 
 }  // namespace tmgcn
@@ -315,11 +327,13 @@ int tmgcn_mtransform_dense_solve_part(const float *src, float *dst, const float 
     return tmgcn::solve_entry<false>(src, dst, halo, T, h, n, ld, ld_halo, band_w, b, stream);
 }
 int tmgcn_mtransform_dense_bwd_range(const float *g_out, float *g_in, int T_out, int halo, int64_t NF,
-                                     const float *band_w, int b, int s_begin, int s_end, void *stream) {
+                                     const float *band_w, int b, int s_begin, int s_end, int acc_begin, void *stream) {
     if (s_begin < 0 || s_end > halo + T_out || s_begin > s_end) {
         tmgcn::set_error("mtransform_dense_bwd_range: bad slice range [%d, %d)", s_begin, s_end);
         return 1;
     }
-    return tmgcn::stencil_entry<true>(g_out, g_out, g_in, T_out, halo, NF, band_w, b, s_begin, s_end, stream);
+    if (acc_begin < 0) acc_begin = 0x7fffffff;
+    return tmgcn::stencil_entry<true>(g_out, g_out, g_in, T_out, halo, NF, band_w, b, s_begin, s_end, stream, 0,
+                                      acc_begin);
 }
 }

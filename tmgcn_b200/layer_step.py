@@ -113,8 +113,11 @@ class LayerStep:
             _p(self.w_f32[t_lo:]), self.band.b, _stream()))
 
     def _spmm(self, csr, x, y, t_lo, t_hi, F):
-        _lib.check(self.lib.tmgcn_spmm_fwd(_p(csr.rowptr[t_lo * self.N:]), _p(csr.col), _p(csr.val), _p(x[t_lo:]),
-                                           _p(y[t_lo:]), t_hi - t_lo, self.N, F, 0, _stream()))
+        # nnz hint: the shard's mean row length decides between the long-row and the short-row kernel
+        hint = csr.nnz * (t_hi - t_lo) // max(self.T, 1)
+        _lib.check(self.lib.tmgcn_spmm_fwd_hint(_p(csr.rowptr[t_lo * self.N:]), _p(csr.col), _p(csr.val),
+                                                _p(x[t_lo:]), _p(y[t_lo:]), t_hi - t_lo, self.N, F, 0, hint,
+                                                _stream()))
 
     def forward(self, H: torch.Tensor, W: torch.Tensor, U: torch.Tensor, comm=None, peer=None) -> torch.Tensor:
         """comm: a sharding.ShardComm -> the forward halo exchange (NCCL) runs on its stream while the slices
@@ -166,6 +169,8 @@ class LayerStep:
         if peer is not None:
             # whatever rewrites H after this call is ordered after every rank's NVLink reads of this step
             peer.wait_reads_done()
+        elif comm is not None:
+            comm.wait_forward_sent()          # ... or after the NCCL send of our last b-1 slices
         self._mark("end")
         return self.out
 
@@ -196,21 +201,29 @@ class LayerStep:
         _lib.check(lib.tmgcn_mtransform_dense_bwd(_p(self.Q), _p(self.Qp), T, self.halo, N * J, _p(self.w_f32),
                                                   self.band.b, st))
         Qp = self.Qp.view(T + self.halo, N, J)
-        lo = 0
+        lo, hi, recv = 0, T + self.halo, None
         if comm is not None:
             h = min(self.band.b - 1, T)
             send = Qp[: self.halo] if self.halo > 0 else None
             recv = self.Qrecv.view(h, N, J) if comm.rank < comm.world - 1 else None
             self._mark("halo_bwd_start")
             comm.start_backward(send, recv)
-            if recv is not None:
-                self._mark("halo_bwd_wait")
-                comm.wait(comm.bwd_recv)
-                Qp[self.halo + T - h:].add_(recv)
             lo = self.halo                       # the halo slices belong to the predecessor: not expanded here
+            if recv is not None:
+                hi = self.halo + T - h           # the last h slices still miss what the successor owes them
+
+        def expand(a, b_):
+            if b_ > a:
+                _lib.check(lib.tmgcn_edge_factor_apply(None, _p(Vu), _p(Qp[a:b_]), _p(dH[a:b_]), None, (b_ - a) * N,
+                                                       Fi, C, None, st))
         self._mark("expand_dH")
-        _lib.check(lib.tmgcn_edge_factor_apply(None, _p(Vu), _p(Qp[lo:]), _p(dH[lo:]), None, (T + self.halo - lo) * N,
-                                               Fi, C, None, st))
+        expand(lo, hi)                           # everything that does not wait for the neighbour first
+        if recv is not None:
+            self._mark("halo_bwd_wait")
+            comm.wait(comm.bwd_recv)
+            self._mark("expand_dH")
+            Qp[hi:].add_(recv)
+            expand(hi, T + self.halo)
         if comm is not None:
             self._mark("grads_wait")
             comm.wait(comm.grads_done)
@@ -247,39 +260,37 @@ class LayerStep:
             self._spmm(self.AtT, dP, dHt, 0, T, self.F_in)
         else:
             comm.start_allreduce([self.dW, self.dU])
+            h = min(self.band.b - 1, T)
+            if comm.rank < comm.world - 1:
+                # P (B2) is dead since dW: what the successor owes our last h slices is received straight into
+                # dH while the whole backward SpMM runs; the main stencil below adds its own part on top
+                recv = dH[self.halo + T - h:]
+                self._mark("halo_bwd_start")
+                comm.start_backward(None, recv)
             # Gradient halo first: the partial sums owed to the predecessor depend only on our first h
             # outputs, so propagate those slices, run the small transposed stencil and put the result on
             # the wire while the remaining slices and the main stencil run.
-            h = min(self.band.b - 1, T)
-            send = None
             self._mark("spmm_bwd")
             self._spmm(self.AtT, dP, dHt, 0, h, self.F_in)
             if self.halo > 0:
-                # P (B2) is dead since dW: the halo slices of dH are produced in place and sent from there
+                # the halo slices of dH are produced in place and sent from there
                 self._mark("stencil_bwd")
                 _lib.check(lib.tmgcn_mtransform_dense_bwd_range(_p(dHt), _p(dH), h, self.halo, NF, _p(self.w_f32),
-                                                                self.band.b, 0, self.halo, st))
-                send = dH[: self.halo]
+                                                                self.band.b, 0, self.halo, -1, st))
                 self._mark("halo_bwd_start")
-                comm.start_backward(send, None)
+                comm.start_backward(dH[: self.halo], None)
             if h < T:
                 self._mark("spmm_bwd")
                 self._spmm(self.AtT, dP, dHt, h, T, self.F_in)
-            if comm.rank < comm.world - 1:
-                # dP (B1) is dead now: receive what the successor owes our last h slices into it
-                recv = self.B1[: h * NF].view(h, N, self.F_in)
-                self._mark("halo_bwd_start")
-                comm.start_backward(None, recv)
-        self._mark("stencil_bwd")
-        _lib.check(lib.tmgcn_mtransform_dense_bwd_range(_p(dHt), _p(dH), T, self.halo, NF, _p(self.w_f32),
-                                                        self.band.b, self.halo if comm is not None else 0,
-                                                        self.halo + T, st))
-        if comm is not None:
             if recv is not None:
                 self._mark("halo_bwd_wait")
                 comm.wait(comm.bwd_recv)
-                self._mark("halo_bwd_add")
-                dH[self.halo + T - recv.shape[0]:].add_(recv)
+        self._mark("stencil_bwd")
+        _lib.check(lib.tmgcn_mtransform_dense_bwd_range(_p(dHt), _p(dH), T, self.halo, NF, _p(self.w_f32),
+                                                        self.band.b, self.halo if comm is not None else 0,
+                                                        self.halo + T,
+                                                        self.halo + T - recv.shape[0] if recv is not None else -1, st))
+        if comm is not None:
             self._mark("grads_wait")
             comm.wait(comm.grads_done)
         self._mark("end")

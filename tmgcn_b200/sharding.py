@@ -142,49 +142,88 @@ class DenseHalo:
             dH[halo + T_own - h:].add_(recv)
 
 
+_NEIGHBOUR_GROUPS = {}
+
+
+def neighbour_groups(world: int):
+    """one process group per pair of neighbouring ranks (i, i+1), created once per process.  Collective: every
+    rank of the default group must call it (the first ShardComm does)."""
+    if world not in _NEIGHBOUR_GROUPS:
+        _NEIGHBOUR_GROUPS[world] = [dist.new_group([i, i + 1]) for i in range(world - 1)]
+    return _NEIGHBOUR_GROUPS[world]
+
+
 class ShardComm:
     """Overlapped halo exchange for `LayerStep`: the NCCL point-to-point traffic runs on its own CUDA
-    stream while the main stream works on the slices that do not need the halo.
+    streams while the main stream works on the slices that do not need the halo.
 
     forward : `start_forward(H)` ships our last b-1 input slices to rank+1 and receives the
               predecessor's into H[:halo]; `main.wait_event(fwd_done)` before the first b-1 outputs.
     backward: `start_backward(send, recv)` ships the partial dH owed to rank-1 and receives what
-              rank+1 owes us; the caller waits on `bwd_recv` and adds it.
-    """
+              rank+1 owes us; the caller waits on `bwd_recv` (and adds it, or lets the stencil accumulate).
 
-    def __init__(self, h: int, rank: int, world: int, device, T_own: Optional[int] = None):
+    Every pair of neighbours talks over its own process group (its own NCCL communicator and stream), and a
+    rank's sends and receives are issued on different CUDA streams: with one communicator all point-to-point
+    operations of a rank are serialised in issue order, and "send to r-1, then receive from r+1" on every
+    rank turns the G-1 independent neighbour transfers into one chain that runs from the last rank down
+    (measured: up to 33 ms of waiting per step for the 9.2 GB gradient halo on 8 GPUs)."""
+
+    def __init__(self, h: int, rank: int, world: int, device, T_own: Optional[int] = None, pair_groups: bool = True):
         self.h, self.rank, self.world = h, rank, world
         if T_own is not None:
             assert_single_hop(T_own, h, world, device)
-        self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self.stream = torch.cuda.Stream(device=device, priority=-1)          # receives, all-reduce
+        self.send_stream = torch.cuda.Stream(device=device, priority=-1)     # sends
         self.fwd_done = torch.cuda.Event()
+        self.fwd_sent = torch.cuda.Event()
         self.bwd_sent = torch.cuda.Event()
         self.bwd_recv = torch.cuda.Event()
         self.grads_done = torch.cuda.Event()
         self.send_pending = False
+        self.fwd_send_pending = False
         self._ready = torch.cuda.Event()
+        self.pg_prev = self.pg_next = None
+        if pair_groups and world > 1:
+            groups = neighbour_groups(world)
+            self.pg_prev = groups[rank - 1] if rank > 0 else None
+            self.pg_next = groups[rank] if rank < world - 1 else None
 
-    def _on_comm_stream(self, fn, done_event):
+    def _group_for(self, peer: int):
+        return self.pg_prev if peer < self.rank else self.pg_next
+
+    def _on_stream(self, stream, fn, done_event):
         main = torch.cuda.current_stream()
         self._ready.record(main)
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(self._ready)
+        with torch.cuda.stream(stream):
+            stream.wait_event(self._ready)
             fn()
-            done_event.record(self.stream)
+            done_event.record(stream)
+
+    def _send(self, t: torch.Tensor, peer: int):
+        dist.isend(t, peer, group=self._group_for(peer)).wait()
+
+    def _recv(self, t: torch.Tensor, peer: int):
+        dist.irecv(t, peer, group=self._group_for(peer)).wait()
 
     def start_forward(self, H: torch.Tensor, T_own: int, halo: int):
         h = min(self.h, T_own)
-        send = H[halo + T_own - h:] if self.rank < self.world - 1 else None
-        recv = H[:halo] if self.rank > 0 and halo > 0 else None
-        self._on_comm_stream(lambda: _chain(send, self.rank + 1, recv, self.rank - 1), self.fwd_done)
+        if self.rank > 0 and halo > 0:
+            recv = H[:halo]
+            self._on_stream(self.stream, lambda: self._recv(recv, self.rank - 1), self.fwd_done)
+        else:
+            self.fwd_done.record(torch.cuda.current_stream())
+        if self.rank < self.world - 1:
+            send = H[halo + T_own - h:]
+            self._on_stream(self.send_stream, lambda: self._send(send, self.rank + 1), self.fwd_sent)
+            self.fwd_send_pending = True
 
     def start_backward(self, send: Optional[torch.Tensor], recv: Optional[torch.Tensor]):
         """The receive and the send complete independently: the step only needs `bwd_recv`; `bwd_sent`
         guards the re-use of the send staging buffer (checked lazily at the next forward)."""
         if recv is not None:
-            self._on_comm_stream(lambda: _chain(None, self.rank - 1, recv, self.rank + 1), self.bwd_recv)
+            self._on_stream(self.stream, lambda: self._recv(recv, self.rank + 1), self.bwd_recv)
         if send is not None:
-            self._on_comm_stream(lambda: _chain(send, self.rank - 1, None, self.rank + 1), self.bwd_sent)
+            self._on_stream(self.send_stream, lambda: self._send(send, self.rank - 1), self.bwd_sent)
             self.send_pending = True
 
     def wait_send_buffer_free(self):
@@ -192,8 +231,14 @@ class ShardComm:
             self.wait(self.bwd_sent)
             self.send_pending = False
 
+    def wait_forward_sent(self):
+        """H's tail was read by the forward send: order whatever rewrites H after it"""
+        if self.fwd_send_pending:
+            self.wait(self.fwd_sent)
+            self.fwd_send_pending = False
+
     def start_allreduce(self, grads: List[torch.Tensor]):
-        self._on_comm_stream(lambda: allreduce_grads(grads), self.grads_done)
+        self._on_stream(self.stream, lambda: allreduce_grads(grads), self.grads_done)
 
     def wait(self, event):
         torch.cuda.current_stream().wait_event(event)
