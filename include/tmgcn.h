@@ -150,10 +150,6 @@ int tmgcn_mtransform_dense_solve_part(const float *src, float *dst, const float 
  * The backward (dX_t = A~_t^T . dY_t) is the same call on the transposed CSR. */
 int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y, int T,
                    int64_t N, int F, int act, void *stream);
-/* same, with the number of stored entries the launch covers (rowptr[T*N] - rowptr[0]; -1 = unknown): graphs with
- * short rows (fewer than 8 entries per row on average) take a software-pipelined kernel. */
-int tmgcn_spmm_fwd_hint(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y, int T,
-                        int64_t N, int F, int act, int64_t nnz, void *stream);
 
 /* ---- (c) feature GEMM  Y = act(P . W) --------------------------------------
  * ref: t.matmul(AtXt, W), ehf:222 / 330 / 344 / 486-489; nonlinearity ehf:332-335.

@@ -290,8 +290,8 @@ def test_spmm_vs_oracle(tg, F):
 
 @pytest.mark.parametrize("F,act", [(128, "none"), (64, "relu"), (96, "selu"), (256, "none")])
 def test_spmm_short_rows(tg, F, act):
-    """graphs with fewer than 8 stored entries per row (the C1-C4 shapes) take the software-pipelined kernel:
-    ragged rows (empty ones, one 70-entry hub) against the oracle, forward and transposed."""
+    """graphs with few stored entries per row (the C1-C4 shapes): ragged rows (many empty ones, one 70-entry hub)
+    against the oracle, forward and transposed, with the activation epilogues."""
     from tmgcn_b200 import ops
     T, N = 5, 900
     g = torch.Generator().manual_seed(F)

@@ -41,7 +41,6 @@ PROTOTYPES = {
     "tmgcn_mtransform_dense_fwd_split": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _i, _p]),
     "tmgcn_mtransform_dense_bwd_range": (_i, [_p, _p, _i, _i, _l, _p, _i, _i, _i, _i, _p]),
     "tmgcn_spmm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _l, _i, _i, _p]),
-    "tmgcn_spmm_fwd_hint": (_i, [_p, _p, _p, _p, _p, _i, _l, _i, _i, _l, _p]),
     "tmgcn_gemm_xw_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),
     "tmgcn_gemm_dw_ws_bytes": (_z, [_i, _i]),
     "tmgcn_gemm_dw_dx_bwd": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),

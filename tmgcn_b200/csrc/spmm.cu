@@ -137,115 +137,6 @@ __global__ void __launch_bounds__(256, MINB) spmm_rows(const int64_t *__restrict
     }
 }
 
-// Short rows (mean < 8 stored entries per row: the Reddit / Bitcoin / chess shapes, where a row's operand
-// traffic no longer hides the dependent chain rowptr -> (col, val) -> gather -> store; measured 34 % of the DRAM
-// floor at C4).  Same group-per-row layout, software-pipelined across the rows a group visits: the row
-// pointers of the NEXT row are requested before the current row is touched and its first (col, val) chunk as
-// soon as the current row's gathers are in flight, and up to 8 gathers are issued per round so a short row
-// needs one round.  Costs registers (up to 85: 3 CTAs per SM), which is why the long-row kernel above stays as it is.
-template <int VEC, int G, int ACT>
-__global__ void __launch_bounds__(256, 3) spmm_rows_short(const int64_t *__restrict__ rowptr,
-                                                          const int32_t *__restrict__ col,
-                                                          const float *__restrict__ val, const float *__restrict__ x,
-                                                          float *__restrict__ y, int64_t n_rows, int64_t N, int F) {
-    using VT = typename VecT<VEC>::T;
-    constexpr int UNROLL = 8 < G ? 8 : G;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (G - 1);
-    const int64_t groups_total = ((int64_t)gridDim.x * blockDim.x) / G;
-    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int Fv = F / VEC;
-    const int64_t n_iter = ceil_div_dev(n_rows, groups_total);
-    // pipeline registers: bounds and first chunk of the row this group handles next
-    int64_t s_n = 0, e_n = 0;
-    int c_n = 0;
-    float v_n = 0.f;
-    if (g0 < n_rows) {
-        s_n = rowptr[g0];
-        e_n = rowptr[g0 + 1];
-        if (s_n + gl < e_n) {
-            c_n = col[s_n + gl];
-            v_n = val[s_n + gl];
-        }
-    }
-    for (int64_t it = 0; it < n_iter; ++it) {
-        const int64_t row = g0 + it * groups_total;
-        const bool live = row < n_rows;
-        const int64_t s = s_n, e = e_n;
-        int c = c_n;
-        float v = v_n;
-        const int64_t nrow = row + groups_total;
-        const bool nlive = nrow < n_rows;
-        s_n = e_n = 0;
-        if (nlive) {                       // next row's bounds: in flight while this row is processed
-            s_n = rowptr[nrow];
-            e_n = rowptr[nrow + 1];
-        }
-        const int64_t xbase = live ? (row / N) * N * (int64_t)Fv : 0;
-        const int len = live ? (int)(e - s) : 0;
-        const int maxlen = G == 32 ? len : __reduce_max_sync(0xffffffffu, len);
-        bool next_loaded = false;
-        for (int fb = 0; fb < Fv; fb += G) {
-            const int f0 = fb + gl;
-            const bool fact = f0 < Fv;
-            VT acc;
-            vzero(acc);
-            const VT *xv = reinterpret_cast<const VT *>(x) + xbase + f0;
-            for (int base = 0; base < maxlen; base += G) {
-                if (base > 0 || fb > 0) {  // later chunks / feature blocks: plain loads
-                    c = 0;
-                    v = 0.f;
-                    if (base + gl < len) {
-                        c = col[s + base + gl];
-                        v = val[s + base + gl];
-                    }
-                }
-                const int cnt = min(G, maxlen - base);
-                for (int j0 = 0; j0 < cnt; j0 += UNROLL) {
-                    VT xs[UNROLL];
-                    float vs[UNROLL];
-#pragma unroll
-                    for (int u = 0; u < UNROLL; ++u) {
-                        const int j = j0 + u;
-                        const int cj = __shfl_sync(0xffffffffu, c, j & (G - 1), G);
-                        vs[u] = __shfl_sync(0xffffffffu, v, j & (G - 1), G);
-                        const bool ok = fact && (base + j < len) && (j < cnt);
-                        if (ok)
-                            xs[u] = __ldg(xv + (int64_t)cj * Fv);
-                        else {
-                            vzero(xs[u]);
-                            vs[u] = 0.f;
-                        }
-                    }
-                    if (!next_loaded) {    // the gathers are in flight: fetch the next row's first chunk behind them
-                        next_loaded = true;
-                        c_n = 0;
-                        v_n = 0.f;
-                        if (nlive && s_n + gl < e_n) {
-                            c_n = col[s_n + gl];
-                            v_n = val[s_n + gl];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UNROLL; ++u) axpy(acc, vs[u], xs[u]);
-                }
-            }
-            if (live && fact) {
-                vact<ACT>(acc);
-                reinterpret_cast<VT *>(y)[row * (int64_t)Fv + f0] = acc;
-            }
-        }
-        if (!next_loaded) {                // empty row (or no feature block): still advance the pipeline
-            c_n = 0;
-            v_n = 0.f;
-            if (nlive && s_n + gl < e_n) {
-                c_n = col[s_n + gl];
-                v_n = val[s_n + gl];
-            }
-        }
-    }
-}
-
 // Skinny operand (W = 4, 6 or 8 floats per row: the 2C-column factor of the low-rank backward for C = 2, 3, 4
 // classes): a row gather is one or two small vector loads, so lanes are spread over the NONZEROS of a row
 // instead of over features.  LPR lanes share a row and a warp takes 32/LPR consecutive rows per iteration, so
@@ -371,7 +262,7 @@ static int launch_skinny(const int64_t *rowptr, const int32_t *col, const float 
 
 template <int VEC, int G>
 static int launch_spmm_act(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y,
-                           int64_t n_rows, int64_t N, int F, int act, bool short_rows, cudaStream_t st) {
+                           int64_t n_rows, int64_t N, int F, int act, cudaStream_t st) {
     const int threads = 256;
     const int64_t groups_per_block = threads / G;
     int64_t blocks = ceil_div(n_rows, groups_per_block);
@@ -379,10 +270,7 @@ static int launch_spmm_act(const int64_t *rowptr, const int32_t *col, const floa
     if (blocks > cap) blocks = cap;
     const unsigned grid = (unsigned)blocks;
 #define TMGCN_LAUNCH(A)                                                                                  \
-    if (short_rows)                                                                                      \
-        spmm_rows_short<VEC, G, A><<<grid, threads, 0, st>>>(rowptr, col, val, x, y, n_rows, N, F);     \
-    else                                                                                                 \
-        spmm_rows<VEC, G, A><<<grid, threads, 0, st>>>(rowptr, col, val, x, y, n_rows, N, F);           \
+    spmm_rows<VEC, G, A><<<grid, threads, 0, st>>>(rowptr, col, val, x, y, n_rows, N, F);               \
     break;
     switch (act) {
         case TMGCN_ACT_NONE: TMGCN_LAUNCH(TMGCN_ACT_NONE)
@@ -397,25 +285,20 @@ static int launch_spmm_act(const int64_t *rowptr, const int32_t *col, const floa
 
 template <int VEC>
 static int launch_spmm_g(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y,
-                         int64_t n_rows, int64_t N, int F, int act, bool sr, cudaStream_t st) {
+                         int64_t n_rows, int64_t N, int F, int act, cudaStream_t st) {
     const int fv = F / VEC;
-    if (fv <= 1) return launch_spmm_act<VEC, 1>(rowptr, col, val, x, y, n_rows, N, F, act, false, st);
-    if (fv <= 2) return launch_spmm_act<VEC, 2>(rowptr, col, val, x, y, n_rows, N, F, act, false, st);
-    if (fv <= 4) return launch_spmm_act<VEC, 4>(rowptr, col, val, x, y, n_rows, N, F, act, false, st);
-    if (fv <= 8) return launch_spmm_act<VEC, 8>(rowptr, col, val, x, y, n_rows, N, F, act, false, st);
-    if (fv <= 16) return launch_spmm_act<VEC, 16>(rowptr, col, val, x, y, n_rows, N, F, act, sr, st);
-    return launch_spmm_act<VEC, 32>(rowptr, col, val, x, y, n_rows, N, F, act, sr, st);
+    if (fv <= 1) return launch_spmm_act<VEC, 1>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 2) return launch_spmm_act<VEC, 2>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 4) return launch_spmm_act<VEC, 4>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 8) return launch_spmm_act<VEC, 8>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (fv <= 16) return launch_spmm_act<VEC, 16>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    return launch_spmm_act<VEC, 32>(rowptr, col, val, x, y, n_rows, N, F, act, st);
 }
 
 }  // namespace tmgcn
 
 extern "C" int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const float *val, const float *x, float *y,
                               int T, int64_t N, int F, int act, void *stream) {
-    return tmgcn_spmm_fwd_hint(rowptr, col, val, x, y, T, N, F, act, -1, stream);
-}
-
-extern "C" int tmgcn_spmm_fwd_hint(const int64_t *rowptr, const int32_t *col, const float *val, const float *x,
-                                   float *y, int T, int64_t N, int F, int act, int64_t nnz, void *stream) {
     using namespace tmgcn;
     TMGCN_REQUIRE(T >= 0 && N >= 0 && F >= 1, "spmm: bad sizes T=%d N=%lld F=%d", T, (long long)N, F);
     const int64_t n_rows = (int64_t)T * N;
@@ -428,14 +311,7 @@ extern "C" int tmgcn_spmm_fwd_hint(const int64_t *rowptr, const int32_t *col, co
     if (F == 4 && a16) return launch_skinny<4>(rowptr, col, val, x, y, T, N, act, st);
     if (F == 6 && a8) return launch_skinny<6>(rowptr, col, val, x, y, T, N, act, st);
     if (F == 8 && a16) return launch_skinny<8>(rowptr, col, val, x, y, T, N, act, st);
-    // short rows: the software-pipelined kernel (only when the caller says how many entries are stored)
-    static int short_mode = -1;          // TMGCN_SPMM_SHORT = 0 / 1 forces the choice (A/B and debugging)
-    if (short_mode == -1) {
-        const char *e = getenv("TMGCN_SPMM_SHORT");
-        short_mode = e ? (e[0] == '1' ? 1 : 0) : 2;
-    }
-    const bool sr = short_mode == 1 || (short_mode == 2 && nnz >= 0 && nnz < 8 * n_rows);
-    if (F % 4 == 0 && a16) return launch_spmm_g<4>(rowptr, col, val, x, y, n_rows, N, F, act, sr, st);
-    if (F % 2 == 0 && a8) return launch_spmm_g<2>(rowptr, col, val, x, y, n_rows, N, F, act, false, st);
-    return launch_spmm_g<1>(rowptr, col, val, x, y, n_rows, N, F, act, false, st);
+    if (F % 4 == 0 && a16) return launch_spmm_g<4>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    if (F % 2 == 0 && a8) return launch_spmm_g<2>(rowptr, col, val, x, y, n_rows, N, F, act, st);
+    return launch_spmm_g<1>(rowptr, col, val, x, y, n_rows, N, F, act, st);
 }

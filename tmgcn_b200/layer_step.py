@@ -113,11 +113,8 @@ class LayerStep:
             _p(self.w_f32[t_lo:]), self.band.b, _stream()))
 
     def _spmm(self, csr, x, y, t_lo, t_hi, F):
-        # nnz hint: the shard's mean row length decides between the long-row and the short-row kernel
-        hint = csr.nnz * (t_hi - t_lo) // max(self.T, 1)
-        _lib.check(self.lib.tmgcn_spmm_fwd_hint(_p(csr.rowptr[t_lo * self.N:]), _p(csr.col), _p(csr.val),
-                                                _p(x[t_lo:]), _p(y[t_lo:]), t_hi - t_lo, self.N, F, 0, hint,
-                                                _stream()))
+        _lib.check(self.lib.tmgcn_spmm_fwd(_p(csr.rowptr[t_lo * self.N:]), _p(csr.col), _p(csr.val), _p(x[t_lo:]),
+                                           _p(y[t_lo:]), t_hi - t_lo, self.N, F, 0, _stream()))
 
     def forward(self, H: torch.Tensor, W: torch.Tensor, U: torch.Tensor, comm=None, peer=None) -> torch.Tensor:
         """comm: a sharding.ShardComm -> the forward halo exchange (NCCL) runs on its stream while the slices

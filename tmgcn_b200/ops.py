@@ -343,8 +343,8 @@ def spmm_raw(csr: SliceCSR, x: torch.Tensor, act: int = 0, out: Optional[torch.T
     if csr.val.dtype != torch.float32:
         raise TypeError("spmm: fp32 CSR values only")
     y = torch.empty_like(x) if out is None else out
-    _lib.check(lib.tmgcn_spmm_fwd_hint(_p(csr.rowptr, _L), _p(csr.col, _I), _p(csr.val, _F), _p(x, _F), _p(y, _F),
-                                       csr.T, csr.N, x.shape[2], act, csr.nnz, _stream()))
+    _lib.check(lib.tmgcn_spmm_fwd(_p(csr.rowptr, _L), _p(csr.col, _I), _p(csr.val, _F), _p(x, _F), _p(y, _F), csr.T,
+                                  csr.N, x.shape[2], act, _stream()))
     return y
 
 
