@@ -77,6 +77,9 @@ def parse():
     ap.add_argument("--no-extras", action="store_true",
                     help="time only the selected workload (no strong_scaling / same_config / parity legs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true",
+                    help="profiling runs: only the warm-up and the timed main steps of the selected workload "
+                         "(no e2e / dense / stage-(a) timing, no extras, no CPU baseline)")
     ap.add_argument("--cpu-nodes", type=int, default=50_000, help="bounded CPU sample: nodes")
     ap.add_argument("--cpu-slices", type=int, default=8, help="bounded CPU sample: slices")
     return ap.parse_args()
@@ -546,7 +549,7 @@ def run_workload(wl, ctx, steps, warmup, full):
         ms_e2e, _ = timed(steps, True)
     alg = step.algorithmic_bytes(ctx.l2)
     ms_dense, dense_stage_times, alg_dense = None, {}, None
-    if step.bwd_mode == "lowrank":     # the general (dense-gradient) layer of SURVEY 8(d): any activation takes it
+    if step.bwd_mode == "lowrank" and not ctx.args.lean:     # the general (dense-gradient) layer of SURVEY 8(d)
         step.bwd_mode = "dense"
         one_step(False)
         ms_dense, _ = timed(steps, False, dense_stage_times)
@@ -699,6 +702,8 @@ def slim(res, peak):
 
 def run_ours(args):
     from tmgcn_b200 import _lib
+    if args.lean:
+        args.no_extras = args.no_cpu_baseline = True
     ctx = Ctx(args)
     _lib.load(build_if_missing=False)
     world, rank = ctx.world, ctx.rank
@@ -716,7 +721,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     wl = resolve_workload(args)
-    res = run_workload(wl, ctx, args.steps, args.warmup, full=True)
+    res = run_workload(wl, ctx, args.steps, args.warmup, full=not args.lean)
 
     strong, same_cfg, fresh = {}, None, None
     if extras:

@@ -12,6 +12,7 @@ The functions are device-agnostic (they only slice, send, receive and add).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -289,6 +290,10 @@ class PeerHalo:
         self.boundary_done = torch.cuda.Event()
         self.reads_done = torch.cuda.Event()
         self._ready = torch.cuda.Event()
+        # neighbour-to-neighbour signals instead of the two all-rank barriers (TMGCN_PEER_SIGNALS=0: barriers):
+        # a rank only has to agree with its predecessor ("your H is complete") and its successor ("I have
+        # finished reading you"), so one slow rank no longer holds up every boundary stencil of the job
+        self.signals = os.environ.get("TMGCN_PEER_SIGNALS", "1") != "0" and hasattr(hdl, "put_signal")
 
     @staticmethod
     def allocate(numel: int, device, group=None):
@@ -307,6 +312,20 @@ class PeerHalo:
         self._ready.record(main)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self._ready)
+            if self.signals:
+                T_MS = 20000                     # a lost signal traps after 20 s instead of hanging the GPU
+                if self.rank < self.world - 1:
+                    self.hdl.put_signal(self.rank + 1, channel=0, timeout_ms=T_MS)   # my H is complete
+                if self.rank > 0:
+                    self.hdl.wait_signal(self.rank - 1, channel=0, timeout_ms=T_MS)  # ... and so is my predecessor's
+                    fn()
+                self.boundary_done.record(self.stream)
+                if self.rank > 0:
+                    self.hdl.put_signal(self.rank - 1, channel=1, timeout_ms=T_MS)   # finished reading rank-1
+                if self.rank < self.world - 1:
+                    self.hdl.wait_signal(self.rank + 1, channel=1, timeout_ms=T_MS)  # rank+1 finished reading me
+                self.reads_done.record(self.stream)
+                return
             self.hdl.barrier(channel=0)          # every rank's H is complete
             if self.rank > 0:
                 fn()
