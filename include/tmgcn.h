@@ -160,6 +160,10 @@ int tmgcn_spmm_fwd(const int64_t *rowptr, const int32_t *col, const float *val, 
  *   dp (R, K) = dy . w^T   and   dw (K, Nf) = p^T . dy  (slice-summed, deterministic).
  * dw_ws: tmgcn_gemm_dw_ws_bytes(K, Nf) bytes of scratch for the per-CTA partials. */
 int tmgcn_gemm_xw_fwd(const float *p, const float *w, float *y, int64_t R, int K, int Nf, int act, void *stream);
+/* y = act(p . w + bias), bias[Nf]: the nn.Linear of the regression head (ref: ehf:418-420); fp32 SIMT kernel.
+ * Its backward is tmgcn_gemm_dw_dx_bwd for dp / dw and the same call with p = ones(R, 1) for dbias = 1^T . dy. */
+int tmgcn_gemm_xw_bias_fwd(const float *p, const float *w, const float *bias, float *y, int64_t R, int K, int Nf,
+                           int act, void *stream);
 size_t tmgcn_gemm_dw_ws_bytes(int K, int Nf);
 int tmgcn_gemm_dw_dx_bwd(const float *p, const float *w, const float *y, const float *dy, float *dp, float *dw,
                          int64_t R, int K, int Nf, int act, void *dw_ws, void *stream);
@@ -208,8 +212,11 @@ int tmgcn_edge_class_sums(const float *dout, const int64_t *inc_ptr, const int64
                           int C, void *stream);
 int tmgcn_edge_factor_apply(const float *y, const float *u, const float *S, float *dy, float *du, int64_t n_rows,
                             int F, int C, void *ws, void *stream);
+/* act != TMGCN_ACT_NONE additionally folds the layer nonlinearity in front of the readout into the same pass:
+ * dy <- dy * act'(y), y being the POST-activation embedding the readout gathered from (ref: ehf:332-335 followed by
+ * ehf:351-355); needs both dy and du (y is in registers for du anyway). */
 int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
-                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *ws,
+                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, int act, void *ws,
                            void *stream);
 
 /* ---- elementwise activation (layer boundary, ref: ehf:332-335) ----------- */

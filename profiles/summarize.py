@@ -16,8 +16,11 @@ def launches(path):
     r = csv.reader(lines)
     hdr = next(r)
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    mi = hdr.index("Metric Name")
     agg = collections.OrderedDict()
     for row in r:
+        if row[mi] != "gpu__time_duration.sum":       # the same pass may carry the DRAM byte counters too
+            continue
         name = row[ki].split("(")[0][:64]
         v = float(row[vi].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(row[ui], 1)
         a = agg.setdefault(name, [0, 0.0])
@@ -31,7 +34,9 @@ def launches(path):
         print(f"{v / 1e6:10.3f} {n:4d} {v / n / 1e6:10.3f} {100 * v / tot:5.1f}%  {k}")
 
 
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -41,13 +46,21 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):      # `ncu -i rep --page raw --csv` already exported on the GPU box
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = csv.reader(out.splitlines())
     hdr = next(r)
     units = next(r)
-    print("# ncu --set full --clock-control none --import-source on; per launch")
+    print("# ncu --set full --clock-control none --import-source on; per launch (first launch of each distinct kernel)")
+    seen = set()
     for row in r:
-        print("\n== " + row[hdr.index("Kernel Name")][:100])
+        name = row[hdr.index("Kernel Name")]
+        if name in seen:
+            continue
+        seen.add(name)
+        print("\n== " + name[:100])
         for w in WANT:
             if w in hdr:
                 i = hdr.index(w)
@@ -100,4 +113,5 @@ def traffic(path, out_json, **cfg):
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "traffic":
-    traffic(sys.argv[2], sys.argv[3], nodes=2_000_000, slices=32, pairs=10_000_000, rho=0.9, band=10, feat=128)
+    traffic(sys.argv[2], sys.argv[3], nodes=2_000_000, slices=32, pairs=10_000_000, rho=0.9, band=10, feat=128,
+            generator="global")

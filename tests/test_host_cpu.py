@@ -139,6 +139,26 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # truthful labelling: the line names the configuration and the steps the CPU arm REALLY ran
+    assert d["steps"] == 1 and d["warmup"] == 0
+    assert "N=1500" in d["config"]["workload"] and "T=4" in d["config"]["workload"]
+    assert d["config"]["extrapolated"] is True and d["config"]["same_config_as_gpu_arm"] is False
+    assert d["ms_per_step"] * d["steps"] * 1e-3 <= d["wall_s"]
+
+
+def test_reference_arm_whole_config_preset():
+    """--preset c1f128 is small enough for the CPU arm to run the WHOLE workload: the line says so (shrunk here
+    through the command-line overrides so the test stays short)."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--preset", "c1f128",
+                        "--nodes", "400", "--pairs", "900", "--total-slices", "6", "--band", "3", "--feat", "8",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["scaling"] == "strong"
+    assert d["config"]["same_config_as_gpu_arm"] is True and d["config"]["extrapolated"] is False
+    assert "N=400" in d["config"]["workload"] and "T=6" in d["config"]["workload"]
 
 
 def test_committed_bench_profile_has_the_contract_keys():

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "tmgcn_mtransform_dense_bwd_range": (_i, [_p, _p, _i, _i, _l, _p, _i, _i, _i, _i, _p]),
     "tmgcn_spmm_fwd": (_i, [_p, _p, _p, _p, _p, _i, _l, _i, _i, _p]),
     "tmgcn_gemm_xw_fwd": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),
+    "tmgcn_gemm_xw_bias_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _i, _p]),
     "tmgcn_gemm_dw_ws_bytes": (_z, [_i, _i]),
     "tmgcn_gemm_dw_dx_bwd": (_i, [_p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
     "tmgcn_gemm_xw_sliced_fwd": (_i, [_p, _p, _p, _i, _l, _i, _i, _i, _p]),
@@ -54,7 +55,7 @@ PROTOTYPES = {
     "tmgcn_edge_factor_ws_bytes": (_z, [_i, _i]),
     "tmgcn_edge_class_sums": (_i, [_p, _p, _p, _p, _l, _i, _p]),
     "tmgcn_edge_factor_apply": (_i, [_p, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
-    "tmgcn_edge_readout_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
+    "tmgcn_edge_readout_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
     "tmgcn_act_fwd": (_i, [_p, _p, _l, _i, _p]),
     "tmgcn_act_bwd": (_i, [_p, _p, _p, _l, _i, _p]),
 }

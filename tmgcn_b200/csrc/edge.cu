@@ -209,7 +209,7 @@ template <int VEC, int NCH, int CM, bool HAS_DY, bool HAS_DU>
 __global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? ((HAS_DY && HAS_DU) ? 2 : (HAS_DU ? 3 : 4)) : 1)
     readout_bwd_kernel(const float *__restrict__ y, const float *__restrict__ u, const float *__restrict__ S, int64_t n_rows,
                                                           float *__restrict__ dy, float *__restrict__ du_partial,
-                                                          int F, int C) {
+                                                          int F, int C, int act) {
     extern __shared__ float sm[];          // us[2F*C] then block reduction scratch red[8 warps][2F*C]
     float *us = sm;
     float *red = sm + 2 * F * C;
@@ -320,6 +320,12 @@ __global__ void __launch_bounds__(256, (NCH == 1 && CM <= 4) ? ((HAS_DY && HAS_D
                         }
                     }
                     if (HAS_DY) {
+                        // layer nonlinearity folded in: dY <- dY * act'(Y), Y being in registers for dU anyway
+                        // (saves the separate elementwise pass: one read of Y and a read + write of dY)
+                        if (HAS_DU && act != TMGCN_ACT_NONE) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) o[v] *= act_grad_rt(yv[r][k][v], act);
+                        }
                         if (VEC == 4)
                             st_stream_f4(reinterpret_cast<float4 *>(dy + row * F + f0),
                                          make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]));
@@ -698,9 +704,20 @@ int tmgcn_edge_class_sums(const float *dout, const int64_t *inc_ptr, const int64
     return after_launch("row_class_sums");
 }
 
+static int factor_apply_impl(const float *y, const float *u, const float *S, float *dy, float *du, int64_t n_rows,
+                             int F, int C, void *ws, int act, void *stream);
+
 int tmgcn_edge_factor_apply(const float *y, const float *u, const float *S, float *dy, float *du, int64_t n_rows,
                             int F, int C, void *ws, void *stream) {
+    return factor_apply_impl(y, u, S, dy, du, n_rows, F, C, ws, TMGCN_ACT_NONE, stream);
+}
+
+// act != none: dy <- dy * act'(y) (needs both outputs: y is only in registers on the fused dY + dU kernel)
+static int factor_apply_impl(const float *y, const float *u, const float *S, float *dy, float *du, int64_t n_rows,
+                             int F, int C, void *ws, int act, void *stream) {
     TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_factor_apply: bad sizes");
+    TMGCN_REQUIRE(act >= 0 && act <= 3, "edge_readout_bwd: unknown activation %d", act);
+    TMGCN_REQUIRE(act == TMGCN_ACT_NONE || (dy && du), "edge_readout_bwd: a fused activation needs both dy and du");
     TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_factor_apply: C=%d outside [1, %d]", C, MAXC);
     cudaStream_t st = (cudaStream_t)stream;
     const int n_u = 2 * F * C;
@@ -780,7 +797,7 @@ int tmgcn_edge_factor_apply(const float *y, const float *u, const float *S, floa
         grid = sm_count() * per_sm;                                                                               \
         const int64_t want = ceil_div(n_rows, 8 * 4);                                                             \
         if (grid > want) grid = (int)(want < 1 ? 1 : want);                                                       \
-        kern<<<grid, 256, smem, st>>>(y, u, S, n_rows, dy, partial, F, C);                                        \
+        kern<<<grid, 256, smem, st>>>(y, u, S, n_rows, dy, partial, F, C, act);                                   \
     }
 #define TMGCN_BY_C(V, K)                                  \
     if (C <= 2) TMGCN_LAUNCH(V, K, 2)                     \
@@ -802,7 +819,7 @@ int tmgcn_edge_factor_apply(const float *y, const float *u, const float *S, floa
 }
 
 int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, const int64_t *inc_ptr,
-                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, void *ws,
+                           const int64_t *perm, float *dy, float *du, int64_t n_rows, int F, int C, int act, void *ws,
                            void *stream) {
     TMGCN_REQUIRE(n_rows >= 0 && F >= 1, "edge_readout_bwd: bad sizes");
     TMGCN_REQUIRE(C >= 1 && C <= MAXC, "edge_readout_bwd: C=%d outside [1, %d]", C, MAXC);
@@ -810,6 +827,6 @@ int tmgcn_edge_readout_bwd(const float *y, const float *u, const float *dout, co
     float *S = (float *)ws;
     const size_t s_bytes = ((size_t)(n_rows > 0 ? n_rows : 0) * 2 * C * sizeof(float) + 255) & ~(size_t)255;
     if (tmgcn_edge_class_sums(dout, inc_ptr, perm, S, n_rows, C, stream)) return 1;
-    return tmgcn_edge_factor_apply(y, u, S, dy, du, n_rows, F, C, ws ? (char *)ws + s_bytes : nullptr, stream);
+    return factor_apply_impl(y, u, S, dy, du, n_rows, F, C, ws ? (char *)ws + s_bytes : nullptr, act, stream);
 }
 }

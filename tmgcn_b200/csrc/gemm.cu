@@ -19,6 +19,9 @@ int gemm_simt_sliced_dp(const float *w, const float *y, const float *dy, float *
 int gemm_simt_sliced_dw(const float *p, const float *y, const float *dy, float *dw, int T, int64_t N, int K, int Nf,
                         int act, cudaStream_t st);
 
+int gemm_simt_bias_fwd(const float *p, const float *w, const float *bias, float *y, int64_t R, int K, int Nf, int act,
+                       cudaStream_t st);
+
 // tensor-core path (gemm_tc.cu)
 bool gemm_tc_eligible(int64_t R, int K, int Nf);
 int gemm_tc_fwd(const float *a, const float *w, float *c, int64_t R, int K, int Nf, int act, bool trans_w,
@@ -48,6 +51,15 @@ int tmgcn_gemm_xw_fwd(const float *p, const float *w, float *y, int64_t R, int K
     cudaStream_t st = (cudaStream_t)stream;
     if (tc_enabled() && gemm_tc_eligible(R, K, Nf)) return gemm_tc_fwd(p, w, y, R, K, Nf, act, false, nullptr, st);
     return gemm_simt_fwd(p, w, y, R, K, Nf, act, st);
+}
+
+int tmgcn_gemm_xw_bias_fwd(const float *p, const float *w, const float *bias, float *y, int64_t R, int K, int Nf,
+                           int act, void *stream) {
+    TMGCN_REQUIRE(R >= 0 && K >= 1 && Nf >= 1, "gemm_xw_bias_fwd: bad sizes R=%lld K=%d Nf=%d", (long long)R, K, Nf);
+    TMGCN_REQUIRE(act >= 0 && act <= 3, "gemm_xw_bias_fwd: unknown activation %d", act);
+    if (R == 0) return 0;
+    TMGCN_REQUIRE(p && w && bias && y, "gemm_xw_bias_fwd: null pointer");
+    return gemm_simt_bias_fwd(p, w, bias, y, R, K, Nf, act, (cudaStream_t)stream);
 }
 
 size_t tmgcn_gemm_dw_ws_bytes(int K, int Nf) { return (size_t)dw_max_chunks() * (size_t)K * (size_t)Nf * sizeof(float); }

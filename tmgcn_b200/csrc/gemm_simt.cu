@@ -20,7 +20,7 @@ template <bool TRANSB, bool GRAD>
 __global__ void __launch_bounds__(256) sgemm_rows(const float *__restrict__ A, const float *__restrict__ Yaux,
                                                   const float *__restrict__ B, float *__restrict__ C, int64_t R,
                                                   int Kd, int Nc, int act, int64_t strideA = 0, int64_t strideB = 0,
-                                                  int64_t strideC = 0) {
+                                                  int64_t strideC = 0, const float *__restrict__ bias = nullptr) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     // grouped form (per-slice weights, ehf:188-191): blockIdx.z selects the slice, every operand advances by its stride
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) sgemm_rows(const float *__restrict__ A, c
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int gc = col0 + tx * 4 + j;
-            if (gc < Nc) C[gr * Nc + gc] = GRAD ? acc[i][j] : act_apply_rt(acc[i][j], act);
+            if (gc < Nc) C[gr * Nc + gc] = GRAD ? acc[i][j] : act_apply_rt(acc[i][j] + (bias ? bias[gc] : 0.f), act);
         }
     }
 }
@@ -228,6 +228,14 @@ int gemm_simt_fwd(const float *p, const float *w, float *y, int64_t R, int K, in
     dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(Nf, BN));
     sgemm_rows<false, false><<<grid, 256, 0, st>>>(p, nullptr, w, y, R, K, Nf, act);
     return after_launch("sgemm_rows<fwd>");
+}
+
+// y = act(p . w + bias): the regression head's nn.Linear (ref: ehf:418-420)
+int gemm_simt_bias_fwd(const float *p, const float *w, const float *bias, float *y, int64_t R, int K, int Nf, int act,
+                       cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(R, BM), (unsigned)ceil_div(Nf, BN));
+    sgemm_rows<false, false><<<grid, 256, 0, st>>>(p, nullptr, w, y, R, K, Nf, act, 0, 0, 0, bias);
+    return after_launch("sgemm_rows<fwd+bias>");
 }
 
 int gemm_simt_dp(const float *w, const float *y, const float *dy, float *dp, int64_t R, int K, int Nf, int act,

@@ -541,16 +541,23 @@ __global__ void __launch_bounds__(32) merge_rows_staged(const int64_t *__restric
 // -- bit for bit what the single-output kernels produce -- and is emitted iff one of its slots with a
 // non-zero weight was hit.  Per output that is ~55 instructions instead of ~97, and the segments are staged
 // once for four outputs.  Staging is a pool (segments packed back to back), not B fixed-size buffers.
-template <int B, int TT>
+template <int B, int TT, bool COUNT>
 __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict__ in_rowptr,
                                                        const int32_t *__restrict__ in_col,
                                                        const float *__restrict__ in_val, int T_out, int halo,
                                                        int64_t N, const double *__restrict__ band_w, int b,
-                                                       int pool, const int64_t *__restrict__ out_rowptr,
+                                                       int pool, int64_t *__restrict__ out_counts,
+                                                       const int64_t *__restrict__ out_rowptr,
                                                        int32_t *__restrict__ out_col, float *__restrict__ out_val) {
+    // COUNT: the plan pass on the same structure -- only the columns are staged (4-byte entries: half the
+    // shared memory per warp, twice the resident warps), a step is the min tree + one predicated cursor step per
+    // source, and output tt counts a column iff one of its non-zero-weight slots was hit.  ~7x fewer
+    // instructions per output than the thread-per-row count pass (whose per-cursor branches diverge) and no
+    // sector over-fetch (that pass read 29.6 GB from DRAM for 3.6 GB of columns).
     constexpr int NS = B - 1 + TT;
+    constexpr int ES = COUNT ? 4 : 8;            // bytes per staged entry
     extern __shared__ __align__(16) uint8_t stage_raw[];
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_raw);   // `pool` entries of {col, val}
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_raw);   // `pool` entries of {col[, val]}
     const int lane = threadIdx.x;
     const int64_t nblk = (N + 31) / 32;
     const int n_groups = (T_out + TT - 1) / TT;
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
         const bool live = i < N;
         const int64_t ic = live ? i : N - 1;
         // weights of output tt on slot k (lag l = B-1-k+tt), zero outside its window / the band / the tensor
-        double w[TT][B];
+        double w[COUNT ? 1 : TT][COUNT ? 1 : B];
         uint32_t nz[TT];                         // slots whose weight for output tt is non-zero
         bool used[NS];
 #pragma unroll
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                 const int sl = halo + t0 + tt - l;
                 double wl = 0.0;
                 if (l < b && t0 + tt < T_out && sl >= 0) wl = band_w[(int64_t)(t0 + tt) * b + l];
-                w[tt][j] = wl;
+                if (!COUNT) w[COUNT ? 0 : tt][COUNT ? 0 : j] = wl;
                 if (wl != 0.0) {
                     nz[tt] |= 1u << (tt + j);
                     used[tt + j] = true;
@@ -611,23 +618,29 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 const int len = off[k + 1] - off[k];
-                uint32_t dst = sbase + (uint32_t)(off[k] + lane) * 8;
-                for (int q = lane; q < len; q += 32, dst += 32 * 8) {
+                uint32_t dst = sbase + (uint32_t)(off[k] + lane) * ES;
+                for (int q = lane; q < len; q += 32, dst += 32 * ES) {
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(in_col + seg0s[k] + q)
                                  : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4), "l"(in_val + seg0s[k] + q)
-                                 : "memory");
+                    if (!COUNT)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4),
+                                     "l"(in_val + seg0s[k] + q)
+                                     : "memory");
                 }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        int32_t *oc[TT];
-        float *ov[TT];
+        int32_t *oc[COUNT ? 1 : TT];
+        float *ov[COUNT ? 1 : TT];
+        int64_t cnt[TT];
 #pragma unroll
         for (int tt = 0; tt < TT; ++tt) {
-            const int64_t ob = (live && t0 + tt < T_out) ? out_rowptr[(int64_t)(t0 + tt) * N + i] : 0;
-            oc[tt] = out_col + ob;
-            ov[tt] = out_val + ob;
+            cnt[tt] = 0;
+            if (!COUNT) {
+                const int64_t ob = (live && t0 + tt < T_out) ? out_rowptr[(int64_t)(t0 + tt) * N + i] : 0;
+                oc[COUNT ? 0 : tt] = out_col + ob;
+                ov[COUNT ? 0 : tt] = out_val + ob;
+            }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -638,11 +651,14 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
             double unused = 0.0;
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-                p[k] = sbase + (uint32_t)(off[k] + (int32_t)(p0s[k] - seg0s[k])) * 8;
-                e[k] = p[k] + (uint32_t)(p1s[k] - p0s[k]) * 8;
+                p[k] = sbase + (uint32_t)(off[k] + (int32_t)(p0s[k] - seg0s[k])) * ES;
+                e[k] = p[k] + (uint32_t)(p1s[k] - p0s[k]) * ES;
                 v[k] = 0;
                 cur[k] = -2;
-                cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], -1, 0.0, unused);
+                if (COUNT)
+                    cursor_step<true, float>(cur[k], v[k], p[k], e[k], -1, 0.0, unused);
+                else
+                    cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], -1, 0.0, unused);
             }
             while (true) {
                 int m = cur[0];
@@ -650,27 +666,36 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                 for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
                 if (m == INT_MAX) break;
                 uint32_t hits = 0;
-                double vd[NS];
+                double vd[COUNT ? 1 : NS];
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     const bool hit = cur[k] == m;
                     hits |= hit ? (1u << k) : 0u;
-                    vd[k] = hit ? (double)__int_as_float(v[k]) : 0.0;      // +0 leaves a chain unchanged
+                    if (!COUNT) vd[COUNT ? 0 : k] = hit ? (double)__int_as_float(v[k]) : 0.0;  // +0 leaves a chain unchanged
                 }
 #pragma unroll
                 for (int tt = 0; tt < TT; ++tt) {
-                    double acc = 0.0;
+                    if (COUNT) {
+                        cnt[tt] += (hits & nz[tt]) ? 1 : 0;
+                    } else {
+                        double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < B; ++j) acc = fma(w[tt][j], vd[tt + j], acc);
-                    if (hits & nz[tt]) {
-                        *oc[tt] = m;
-                        *ov[tt] = (float)acc;
-                        ++oc[tt];
-                        ++ov[tt];
+                        for (int j = 0; j < B; ++j) acc = fma(w[COUNT ? 0 : tt][COUNT ? 0 : j], vd[COUNT ? 0 : tt + j], acc);
+                        if (hits & nz[tt]) {
+                            *oc[COUNT ? 0 : tt] = m;
+                            *ov[COUNT ? 0 : tt] = (float)acc;
+                            ++oc[COUNT ? 0 : tt];
+                            ++ov[COUNT ? 0 : tt];
+                        }
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NS; ++k) cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
+                for (int k = 0; k < NS; ++k) {
+                    if (COUNT)
+                        cursor_step<true, float>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
+                    else
+                        cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
+                }
             }
         } else {
             // hub blocks: the same merge on global memory
@@ -683,7 +708,7 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                 ge[k] = p1s[k];
                 const bool in = gp[k] < ge[k];
                 cur[k] = in ? in_col[gp[k]] : INT_MAX;
-                v[k] = in ? in_val[gp[k]] : 0.f;
+                v[k] = (!COUNT && in) ? in_val[gp[k]] : 0.f;
             }
             while (true) {
                 int m = cur[0];
@@ -691,33 +716,42 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                 for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
                 if (m == INT_MAX) break;
                 uint32_t hits = 0;
-                double vd[NS];
+                double vd[COUNT ? 1 : NS];
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     const bool hit = cur[k] == m;
                     hits |= hit ? (1u << k) : 0u;
-                    vd[k] = hit ? (double)v[k] : 0.0;
+                    if (!COUNT) vd[COUNT ? 0 : k] = hit ? (double)v[k] : 0.0;
                     gp[k] += hit ? 1 : 0;
                 }
 #pragma unroll
                 for (int tt = 0; tt < TT; ++tt) {
-                    double acc = 0.0;
+                    if (COUNT) {
+                        cnt[tt] += (hits & nz[tt]) ? 1 : 0;
+                    } else {
+                        double acc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < B; ++j) acc = fma(w[tt][j], vd[tt + j], acc);
-                    if (hits & nz[tt]) {
-                        *oc[tt] = m;
-                        *ov[tt] = (float)acc;
-                        ++oc[tt];
-                        ++ov[tt];
+                        for (int j = 0; j < B; ++j) acc = fma(w[COUNT ? 0 : tt][COUNT ? 0 : j], vd[COUNT ? 0 : tt + j], acc);
+                        if (hits & nz[tt]) {
+                            *oc[COUNT ? 0 : tt] = m;
+                            *ov[COUNT ? 0 : tt] = (float)acc;
+                            ++oc[COUNT ? 0 : tt];
+                            ++ov[COUNT ? 0 : tt];
+                        }
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     const bool in = gp[k] < ge[k];
                     cur[k] = in ? in_col[gp[k]] : INT_MAX;
-                    v[k] = in ? in_val[gp[k]] : 0.f;
+                    if (!COUNT) v[k] = in ? in_val[gp[k]] : 0.f;
                 }
             }
+        }
+        if (COUNT) {
+#pragma unroll
+            for (int tt = 0; tt < TT; ++tt)
+                if (live && t0 + tt < T_out) out_counts[(int64_t)(t0 + tt) * N + i] = cnt[tt];
         }
         __syncwarp();                            // the pool is reused by the next task
     }
@@ -742,10 +776,11 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
     }
     const int threads = 128;
     const unsigned grid = (unsigned)ceil_div((int64_t)T_out * N, threads);
-    constexpr size_t entry = StageEntry<COUNT_ONLY, VT>::SIZE;
+    // staged entry size of the FILL pass (the count pass takes the same decisions so both run the same variant)
+    constexpr size_t entry = COUNT_ONLY ? 8 : StageEntry<COUNT_ONLY, VT>::SIZE;
     int sel = 0;
     int cap = 0;
-    if (!COUNT_ONLY && forced != 0) {
+    if (forced != 0) {
         int bb = 2;                                                         // the template width b rounds up to
         for (const int cand : {2, 4, 6, 8, 10, 12, 16, 20, 24, 32})
             if (b <= cand) {
@@ -774,7 +809,7 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
             }
         }
     }
-    if constexpr (!COUNT_ONLY && sizeof(VT) == 4) {
+    if constexpr (sizeof(VT) == 4) {
         static int tiled = -1;
         if (tiled < 0) {
             const char *e = getenv("TMGCN_MERGE_TT");
@@ -783,18 +818,20 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
         // the tiled kernel pays off when a warp's B-1+4 source segments fit its staging pool (sel >= 1 says the
         // per-slice staged kernel would fit too); forced variants (TMGCN_MERGE_STAGED) bypass it
         if (tiled && b <= 12 && forced < 0 && sel >= 1 && T_out >= 4) {
-            const int pool = (38 * 1024) / 8;                               // entries of {col, val}
-            const size_t smem = (size_t)pool * 8;
+            const int pool = (38 * 1024) / 8;                               // staged entries ({col, val}; count: col)
+            const size_t smem = (size_t)pool * (COUNT_ONLY ? 4 : 8);
             const int64_t n_tasks = (int64_t)ceil_div(T_out, 4) * ceil_div(N, (int64_t)32);
-            int64_t g = (int64_t)sm_count() * (int64_t)((220 * 1024) / (smem + 1024));
+            int per_sm = (int)((220 * 1024) / (smem + 1024));
+            if (per_sm > 16) per_sm = 16;
+            int64_t g = (int64_t)sm_count() * per_sm;
             if (g > n_tasks) g = n_tasks;
 #define TMGCN_TILED(BB)                                                                                          \
     if (b <= BB) {                                                                                               \
-        auto kern = merge_rows_tiled<BB, 4>;                                                                     \
+        auto kern = merge_rows_tiled<BB, 4, COUNT_ONLY>;                                                         \
         TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        kern<<<(unsigned)g, 32, smem, st>>>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b, pool,          \
-                                            out_rowptr, out_col, out_val);                                       \
-        return after_launch("merge_rows_tiled<fill>");                                                           \
+        kern<<<(unsigned)g, 32, smem, st>>>(in_rowptr, in_col, (const float *)in_val, T_out, halo, N, band_w, b, \
+                                            pool, out_counts, out_rowptr, out_col, (float *)out_val);            \
+        return after_launch(COUNT_ONLY ? "merge_rows_tiled<count>" : "merge_rows_tiled<fill>");                  \
     }
             TMGCN_TILED(2) TMGCN_TILED(4) TMGCN_TILED(6) TMGCN_TILED(8) TMGCN_TILED(10) TMGCN_TILED(12)
 #undef TMGCN_TILED

@@ -243,11 +243,9 @@ class LayerStep:
         dH = self._view(self.B2, T + self.halo, self.F_in)
         NF = N * self.F_in
         self._mark("readout_bwd")
+        # the layer nonlinearity's derivative is folded into the same pass (dY <- dY * act'(Y))
         _lib.check(lib.tmgcn_edge_readout_bwd(_p(Y), _p(U), _p(dOut), _p(inc_ptr), _p(perm), _p(dY), _p(self.dU),
-                                              T * N, self.F_out, self.C, _p(self.du_ws), st))
-        if self.act:
-            self._mark("act_bwd")
-            _lib.check(lib.tmgcn_act_bwd(_p(Y), _p(dY), _p(dY), dY.numel(), self.act, st))
+                                              T * N, self.F_out, self.C, self.act, _p(self.du_ws), st))
         self._mark("gemm_bwd")
         _lib.check(lib.tmgcn_gemm_dw_dx_bwd(_p(P), _p(W), None, _p(dY), _p(dP), _p(self.dW), T * N, self.F_in,
                                             self.F_out, 0, _p(self.dw_ws), st))

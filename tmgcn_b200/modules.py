@@ -253,7 +253,7 @@ class EmbeddingGCN_reg(_Base):
         Y = ops.gemm_xw(self.AtXt, self.W) if self.condensed_W else ops.gemm_xw_sliced(self.AtXt, self.W)
         if self.use_Minv:                                                            # ehf:415-417
             Y = ops.mtransform_dense_inv(Y, self.band)
-        out = ops.gemm_xw(Y, self.lin1.weight.t().contiguous()) + self.lin1.bias     # (T, N, 1)
+        out = ops.linear(Y, self.lin1.weight.t().contiguous(), self.lin1.bias)       # (T, N, 1), ehf:418-420
         return out.squeeze(2)
 
 

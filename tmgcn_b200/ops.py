@@ -442,7 +442,7 @@ def readout_bwd_raw(y2d, plan: EdgePlan, u, dout, need_dy=True, need_du=True):
     ws = _ws(lib.tmgcn_edge_readout_bwd_ws_bytes(y2d.shape[0], F, Cc))
     if need_dy or need_du:
         _lib.check(lib.tmgcn_edge_readout_bwd(_p(y2d), _p(u), _p(dout), _p(inc_ptr), _p(perm), _p(dy), _p(du),
-                                              y2d.shape[0], F, Cc, _p(ws), _stream()))
+                                              y2d.shape[0], F, Cc, 0, _p(ws), _stream()))
     return dy, du
 
 
@@ -734,6 +734,40 @@ class _GemmSliced(torch.autograd.Function):
         _lib.check(lib.tmgcn_gemm_sliced_bwd(_p(p, _F), _p(w, _F), _p(y), _p(g, _F), _p(dp), _p(dw), T, N, K, Nf,
                                              ctx.act, _stream()))
         return dp, dw, None
+
+
+class _Linear(torch.autograd.Function):
+    """y = p @ w + bias in one launch (the bias rides in the GEMM epilogue); backward: dp, dw by the GEMM backward
+    kernels and dbias = 1^T dy as a (1 x Nf) dW product."""
+
+    @staticmethod
+    def forward(ctx, p, w, bias):
+        lib = _lib.load()
+        p, w, bias = _f32(p), _f32(w), _f32(bias)
+        K, Nf = w.shape
+        R = p.numel() // K
+        y = torch.empty(tuple(p.shape[:-1]) + (Nf,), dtype=torch.float32, device=p.device)
+        _lib.check(lib.tmgcn_gemm_xw_bias_fwd(_p(p, _F), _p(w, _F), _p(bias, _F), _p(y, _F), R, K, Nf, 0, _stream()))
+        ctx.save_for_backward(p, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        p, w = ctx.saved_tensors
+        g = _f32(g)
+        dp, dw = gemm_bwd_raw(p, w, None, g, 0, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        db = None
+        if ctx.needs_input_grad[2]:
+            R = g.numel() // w.shape[1]
+            ones = torch.ones(R, 1, dtype=torch.float32, device=g.device)
+            _, db = gemm_bwd_raw(ones, torch.empty(1, w.shape[1], device=g.device), None, g, 0, False, True)
+            db = db.reshape(-1)
+        return dp, dw, db
+
+
+def linear(p, w, bias):
+    """p @ w + bias (ref: nn.Linear at ehf:418-420; w is (K, Nf) = weight^T), differentiable."""
+    return _Linear.apply(p, w, bias)
 
 
 def gemm_xw_sliced(p, w, act=None):
