@@ -114,26 +114,42 @@ class SliceCSR:
     @staticmethod
     def from_slice_list(slices: Sequence[torch.Tensor], N: int, dtype=torch.float32) -> "SliceCSR":
         """Python list of T 2-D sparse COO matrices (the reference's `At` argument,
-        ref: experiment_bitcoin_our.py:53-56) -> device CSR-of-slices."""
-        ts, rs, cs, vs = [], [], [], []
+        ref: experiment_bitcoin_our.py:53-56) -> device CSR-of-slices.  The list lives on the host in the
+        reference's scripts, and this conversion is most of a fresh-input call (ehf:212-215), so it moves as
+        little as it can: (row, col) as int32 and the values in the target dtype, 12 bytes per entry instead of
+        the 32 of an int64 (t, i, j) + fp64 COO; the time index is rebuilt on the device from the slice lengths."""
+        lib = _lib.load()
+        dev = _dev()
+        T = len(slices)
+        ijs, vs, lens = [], [], []
         for t, A in enumerate(slices):
             if A.layout != torch.sparse_coo:
                 raise TypeError("every slice must be a sparse COO tensor")
             A = A if A.is_coalesced() else A.coalesce()
-            ij = A._indices()
-            if ij.numel() and int(ij.max()) >= N:
-                raise ValueError(f"slice {t} has an index >= N={N}")
-            ts.append(torch.full((ij.shape[1],), t, dtype=torch.int64, device=ij.device))
-            rs.append(ij[0])
-            cs.append(ij[1])
+            ijs.append(A._indices())
             vs.append(A._values())
-        if not ts:
-            idx = torch.zeros(3, 0, dtype=torch.int64)
-            val = torch.zeros(0, dtype=torch.float64)
-        else:
-            idx = torch.stack([torch.cat(ts), torch.cat(rs), torch.cat(cs)])
-            val = torch.cat(vs)
-        return SliceCSR.from_coo(idx, val, len(slices), N, dtype)
+            lens.append(A._nnz())
+        if T == 0 or sum(lens) == 0:
+            return SliceCSR.from_coo(torch.zeros(3, 0, dtype=torch.int64), torch.zeros(0, dtype=torch.float64), T, N, dtype)
+        ij = torch.cat(ijs, dim=1)
+        if N >= 2 ** 31:
+            raise ValueError("N must fit int32")
+        ij = ij.to(torch.int32).to(dev, non_blocking=True)                   # (2, nnz) int32
+        val = torch.cat(vs).to(dtype).to(dev, non_blocking=True).contiguous()
+        lens_d = torch.tensor(lens, dtype=torch.int64).to(dev)
+        # range and order checks (what from_coo does), on the device
+        lo, hi = ij.min(), ij.max()
+        if int(lo) < 0 or int(hi) >= N:
+            raise ValueError(f"a slice has an index outside [0, {N})")
+        t_idx = torch.repeat_interleave(torch.arange(T, device=dev, dtype=torch.int64), lens_d)
+        flat = (t_idx * N + ij[0]).contiguous()
+        key = flat * N + ij[1]
+        if bool((key[1:] <= key[:-1]).any()):
+            raise ValueError("from_slice_list: slices must be coalesced (strictly ascending (i, j) order)")
+        del key, t_idx
+        rowptr = torch.empty(T * N + 1, dtype=torch.int64, device=dev)
+        _lib.check(lib.tmgcn_rowptr_from_sorted_rows(_p(flat), flat.numel(), T * N, _p(rowptr), _stream()))
+        return SliceCSR(T, N, rowptr, ij[1].contiguous(), val)
 
     def time_window(self, start: int, end: int) -> "SliceCSR":
         """slices [start, end) re-based to 0 (ref: func_create_sparse, read_data.py:174-183)"""
