@@ -172,6 +172,22 @@ def test_committed_bench_profile_has_the_contract_keys():
     assert d["vs_baseline"] is None                      # BASELINE.md holds no published number for this metric
 
 
+def test_committed_round2_profile_has_the_new_legs():
+    import json
+    with open(os.path.join(ROOT, "profiles", "r02_bench_1gpu.json")) as f:
+        d = json.loads(f.read().strip().splitlines()[-1])
+    assert _BENCH_KEYS | {"clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "dense", "strong_scaling",
+                          "same_config", "extra"} <= set(d)
+    assert d["scaling"] == "weak" and set(d["strong_scaling"]) == {"c5cut", "c4"}
+    assert all(v["scaling"] == "strong" for v in d["strong_scaling"].values())
+    assert d["extra"]["same_config_ratio"] == d["same_config"]["ratio"] > 1
+    assert d["dense"]["ms_per_step"] > d["ms_per_step"] and "spmm_bwd" in d["dense"]["stages"]
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    with open(os.path.join(ROOT, "profiles", "r02_bench_8gpu.json")) as f:
+        d8 = json.loads(f.read().strip().splitlines()[-1])
+    assert d8["n_gpus"] == 8 and d8["parity_multi_gpu"]["ok"] is True and len(d8["stages_ms_per_rank"]) == 8
+
+
 def test_header_is_plain_c(tmp_path):
     """include/tmgcn.h is the FFI contract: it must compile as C99 (and C++) on its own, and a C program linked
     against the shared library must resolve the symbols it declares (no GPU needed to call the version query)."""
