@@ -535,24 +535,35 @@ def run_workload(wl, ctx, steps, warmup, full):
             ms = float(tms.item())
         return ms, _lib.launch_count() - n0
 
+    def note(msg):           # progress on stderr (rank 0): which leg a failure belongs to
+        if rank == 0:
+            print(f"[bench] {wl['name']} x{world}: {msg}", file=sys.stderr, flush=True)
+    note(f"setup done (T_own={T_own}, nnz={At.nnz}, halo={halo_mode}, bwd={step.bwd_mode})")
     W_ = max(warmup, 3)
     for _ in range(W_):
         one_step(False)
+    torch.cuda.synchronize()
+    note("warm-up done")
     sampler = ClockSampler(ctx.local) if (rank == 0 and full) else None
     stage_times = {}
     ms, launches = timed(steps, False, stage_times)
     host_enqueue_ms = host_ms[0]
+    note(f"main timed: {ms / steps:.3f} ms/step")
     clocks = sampler.stop() if sampler else None
     ms_e2e = None
     if full:
         one_step(True)
         ms_e2e, _ = timed(steps, True)
+        note(f"e2e timed: {ms_e2e / steps:.3f} ms/step")
     alg = step.algorithmic_bytes(ctx.l2)
     ms_dense, dense_stage_times, alg_dense = None, {}, None
     if step.bwd_mode == "lowrank" and not ctx.args.lean:     # the general (dense-gradient) layer of SURVEY 8(d)
         step.bwd_mode = "dense"
         one_step(False)
+        torch.cuda.synchronize()
+        note("dense warm-up done")
         ms_dense, _ = timed(steps, False, dense_stage_times)
+        note(f"dense timed: {ms_dense / steps:.3f} ms/step")
         alg_dense = step.algorithmic_bytes(ctx.l2)
         step.bwd_mode = "lowrank"
 
