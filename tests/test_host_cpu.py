@@ -117,6 +117,28 @@ def test_synth_generator_matches_reference_preparation():
     assert shared > 0.55
 
 
+def test_global_synthetic_graph_is_partition_independent():
+    """synth_slices_global: a rank generates exactly its window of ONE dynamic graph (the strong-scaling runs keep
+    the total work fixed whatever the number of ranks), the slice sizes stay at ~2m + N stored entries and
+    consecutive slices share ~rho of their pairs."""
+    from tmgcn_b200 import synth
+    N, m, rho = 300, 900, 0.9
+    whole = list(synth.synth_slices_global(N, 0, 90, m, rho, seed=3))
+    part = list(synth.synth_slices_global(N, 83, 90, m, rho, seed=3))          # beyond the lifetime cap (66)
+    for a, b_ in zip(whole[83:], part):
+        assert all(torch.equal(x, y) for x, y in zip(a, b_))
+    sizes = [r.numel() for r, _, _ in whole]
+    assert min(sizes) > 0.85 * (2 * m + N) and max(sizes) < 1.1 * (2 * m + N)  # stationary, no drift
+    keys = [set((r * N + c).tolist()) for r, c, _ in whole[40:44]]
+    off = [k - {i * N + i for i in range(N)} for k in keys]
+    shared = len(off[0] & off[1]) / len(off[0])
+    assert 0.8 < shared < 0.97
+    assert synth.life_cap(0.0) == 1 and synth.life_cap(0.9) == 66
+    # the CSR / COO front ends take the same windows
+    i1, v1 = synth.synth_coo(N, 4, m, rho, seed=3, t_start=83)
+    assert torch.equal(i1[1][i1[0] == 0], part[0][0]) and torch.equal(v1[i1[0] == 0], part[0][2])
+
+
 # ---------------------------------------------------------------- bench.py contract
 _BENCH_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                "vs_baseline", "dtype", "data", "config"}

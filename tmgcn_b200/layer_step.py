@@ -94,6 +94,14 @@ class LayerStep:
             self.fac_ws = ops._ws(self.lib.tmgcn_edge_factor_ws_bytes(max(F_in, F_out), C))
         self.hook: Optional[Callable[[str], None]] = None   # called before each stage (bench timing)
 
+    @staticmethod
+    def _check_f32(**tensors):
+        # raw pointers go straight to fp32 kernels: another dtype would be silently reinterpreted
+        for name, t in tensors.items():
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise TypeError(f"LayerStep: {name} must be a contiguous float32 CUDA tensor (got {t.dtype}, "
+                                f"{'cuda' if t.is_cuda else 'cpu'})")
+
     def _view(self, buf, T, F):
         return buf[: T * self.N * F].view(T, self.N, F)
 
@@ -124,6 +132,8 @@ class LayerStep:
         lib, T, N, st = self.lib, self.T, self.N, _stream()
         h_in = 0 if peer is not None else self.halo
         assert H.shape == (T + h_in, N, self.F_in) and H.is_contiguous()
+        self._check_f32(H=H, W=W, U=U)
+        assert W.shape == (self.F_in, self.F_out) and U.shape == (2 * self.F_out, self.C)
         Ht = self._view(self.B1, T, self.F_in)
         P = self._view(self.B2, T, self.F_in)
         Y = self._view(self.B1, T, self.F_out)
@@ -231,6 +241,8 @@ class LayerStep:
         """-> dH (halo + T, N, F_in) view of a work buffer, dW, dU.  With `comm` the partial-gradient halo
         and the dW/dU all-reduce overlap the main backward stencil; dH[halo:] is then complete (and dH[:halo]
         is what was sent to the predecessor / unspecified)."""
+        self._check_f32(dOut=dOut, W=W, U=U)
+        assert dOut.shape == (self.plan.E, self.C)
         if self.bwd_mode == "lowrank":
             return self._backward_lowrank(dOut, W, U, comm)
         lib, T, N, st = self.lib, self.T, self.N, _stream()
