@@ -655,7 +655,7 @@ def module_fresh_input_leg(args, ctx, with_cpu=True, calls=5):
     edges = torch.from_numpy(ai[:, pick.numpy()])
     torch.manual_seed(SEED)
     gcn = tg.EmbeddingGCN(At, X, edges, M, hidden_feat=[F1, C], condensed_W=True, use_Minv=False)
-    h2d = nnz * (3 * 8 + 8) + X.numel() * 8 + edges.numel() * 8
+    h2d = nnz * (4 + 4 + 4) + T * 8 + X.numel() * 8 + edges.numel() * 8     # (row, col) int32 + fp32 value per entry
     d2h = E * C * 4
     with torch.no_grad():
         for _ in range(2):
