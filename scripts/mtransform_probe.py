@@ -1,0 +1,99 @@
+"""Sparse M-transform (stage a) at the benchmark shard, phase by phase: count pass, scan, fill pass -- with the
+union-list fill (default) and with the merging fill (TMGCN_MERGE_UNION=0), each in its own process because the
+choice is latched on first use.  Both must produce identical bits.
+
+    python scripts/mtransform_probe.py [--nodes N --slices T --pairs M --band B] > gpurun_out/r02_mtransform_probe.json
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def child(a):
+    sys.path.insert(0, ROOT)
+    import torch
+    import tmgcn_b200 as tg
+    from tmgcn_b200 import _lib, ops, synth
+    from tmgcn_b200.ops import _p, _stream
+    lib = _lib.load()
+    N, T, b = a.nodes, a.slices, a.band
+    A = synth.synth_csr(N, T, a.pairs, a.rho, seed=20261017, t_start=0)
+    if a.f64:
+        A = tg.SliceCSR(A.T, A.N, A.rowptr, A.col, A.val.double())
+    band = tg.Band(tg.create_matrix_M(T, b))
+    w = band.device_weights(0, T, torch.float64)
+    dev = A.rowptr.device
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    best = None
+    out = None
+    for _ in range(a.reps):
+        counts = torch.empty(T * N, dtype=torch.int64, device=dev)
+        ws_bytes = int(lib.tmgcn_mtransform_sparse_ws_bytes(T, 0, N, b, A.nnz))
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev) if ws_bytes else None
+        torch.cuda.synchronize()
+        ev[0].record()
+        _lib.check(lib.tmgcn_mtransform_sparse_plan_ws(_p(A.rowptr), _p(A.col), T, 0, N, _p(w), b, _p(counts), _p(ws),
+                                                       ws_bytes, _stream()))
+        ev[1].record()
+        rowptr = ops.exclusive_scan(counts)
+        nnz = int(rowptr[-1].item())
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=A.val.dtype, device=dev)
+        ev[2].record()
+        _lib.check(lib.tmgcn_mtransform_sparse_run_ws(_p(A.rowptr), _p(A.col), _p(A.val), T, 0, N, _p(w), b, _p(rowptr),
+                                                      _p(col), _p(val), 1 if a.f64 else 0, _p(ws), ws_bytes, _stream()))
+        ev[3].record()
+        torch.cuda.synchronize()
+        t = {"count_ms": ev[0].elapsed_time(ev[1]), "scan_alloc_ms": ev[1].elapsed_time(ev[2]),
+             "fill_ms": ev[2].elapsed_time(ev[3]), "total_ms": ev[0].elapsed_time(ev[3])}
+        if best is None or t["total_ms"] < best["total_ms"]:
+            best = t
+        n_over = int(ws[:4].view(torch.int32).item()) if ws is not None else None
+        out = (rowptr, col, val)
+        del counts, ws
+    rowptr, col, val = out
+    wgt = torch.arange(col.numel(), device=dev, dtype=torch.int64) % 97 + 1
+    alg = 8.0 * A.nnz + 4.0 * (N + 1) * T + 8.0 * col.numel() + 4.0 * (N + 1) * T
+    res = {"union": os.environ.get("TMGCN_MERGE_UNION", "1") != "0", "f64": bool(a.f64), "in_nnz": A.nnz,
+           "out_nnz": int(col.numel()), "ws_bytes": ws_bytes, "overflowed_tasks": n_over,
+           "n_tasks": ((T + 3) // 4) * ((N + 31) // 32), **best, "algorithmic_bytes": alg,
+           "GB/s": alg / best["total_ms"] * 1e-6,
+           "checksum": [int(rowptr.sum()), int((col.to(torch.int64) * wgt).sum()),
+                        repr(float((val.double() * wgt.double()).sum()))]}
+    print(json.dumps(res))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nodes", type=int, default=2_000_000)
+    ap.add_argument("--slices", type=int, default=32)
+    ap.add_argument("--pairs", type=int, default=10_000_000)
+    ap.add_argument("--rho", type=float, default=0.9)
+    ap.add_argument("--band", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--f64", action="store_true")
+    ap.add_argument("--child", action="store_true")
+    a = ap.parse_args()
+    if a.child:
+        return child(a)
+    runs = {}
+    for name, flag in (("union_fill", "1"), ("merging_fill", "0")):
+        env = dict(os.environ, TMGCN_MERGE_UNION=flag)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"] + sys.argv[1:], env=env,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            runs[name] = {"error": r.stderr[-2000:]}
+        else:
+            runs[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    same = ("checksum" in runs["union_fill"] and runs["union_fill"].get("checksum") == runs["merging_fill"].get("checksum"))
+    print(json.dumps({"workload": vars(a), "identical_bits": same, **runs}))
+
+
+if __name__ == "__main__":
+    main()

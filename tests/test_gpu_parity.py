@@ -130,7 +130,8 @@ def test_mtransform_sparse_vs_oracle(tg, T, N, m, rho, b, norm):
 
 def test_mtransform_sparse_fill_variants_agree(tg):
     """the fill-pass variants of the sparse M-transform (thread per row; shared-memory staged with 1, 2 or 4
-    lanes per row; the automatic choice; the time-tiled kernel) in subprocesses, because the choice is latched on first use.  All of
+    lanes per row; the automatic choice; the time-tiled kernels with the union-list fill and with the merging
+    fill) in subprocesses, because the choice is latched on first use.  All of
     them sum a row's contributions in the same order, so indices AND values are bit-identical.  Hub rows
     overflow the staging capacity and take the kernel's global-memory path."""
     import os
@@ -155,12 +156,16 @@ for b in (2, 5, 10, 24):
               repr(float((out.val.double() * w).sum())))
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for flag in ("0", "1", "2", "4", None, "tiled", "untiled"):
+    for flag in ("0", "1", "2", "4", None, "tiled", "untiled", "merging"):
         env = dict(os.environ)
         env.pop("TMGCN_MERGE_STAGED", None)
         env.pop("TMGCN_MERGE_TT", None)
+        env.pop("TMGCN_MERGE_UNION", None)
         if flag == "tiled":
-            env["TMGCN_MERGE_TT"] = "1"         # four output slices per merge pass (fp32 values, b <= 12): the default
+            env["TMGCN_MERGE_TT"] = "1"         # four output slices per merge pass (b <= 12): the default, with the
+                                                # union-list fill (count pass records the pattern, fill never merges)
+        elif flag == "merging":
+            env["TMGCN_MERGE_UNION"] = "0"      # the same count pass, fill pass merges again (round-1/2 kernel)
         elif flag == "untiled":
             env["TMGCN_MERGE_TT"] = "0"         # the per-slice kernels, chosen by row length
         elif flag is not None:
@@ -168,7 +173,7 @@ for b in (2, 5, 10, 24):
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
         outs[flag] = [ln.split() for ln in r.stdout.strip().splitlines()]
         assert len(outs[flag]) == 8
-    for flag in ("1", "2", "4", None, "tiled", "untiled"):
+    for flag in ("1", "2", "4", None, "tiled", "untiled", "merging"):
         assert outs[flag] == outs["0"], flag
 
 

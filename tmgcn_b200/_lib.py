@@ -26,6 +26,9 @@ PROTOTYPES = {
     "tmgcn_rowptr_from_sorted_rows": (_i, [_p, _l, _l, _p, _p]),
     "tmgcn_mtransform_sparse_plan": (_i, [_p, _p, _i, _i, _l, _p, _i, _p, _p]),
     "tmgcn_mtransform_sparse_run": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _p, _p, _p, _i, _p]),
+    "tmgcn_mtransform_sparse_ws_bytes": (_z, [_i, _i, _l, _i, _l]),
+    "tmgcn_mtransform_sparse_plan_ws": (_i, [_p, _p, _i, _i, _l, _p, _i, _p, _p, _z, _p]),
+    "tmgcn_mtransform_sparse_run_ws": (_i, [_p, _p, _p, _i, _i, _l, _p, _i, _p, _p, _p, _i, _p, _z, _p]),
     "tmgcn_csr_transpose_ws_bytes": (_z, [_l, _l, _i]),
     "tmgcn_csr_transpose_plan": (_i, [_p, _p, _i, _l, _p, _p]),
     "tmgcn_csr_transpose_run": (_i, [_p, _p, _p, _i, _l, _p, _p, _p, _i, _p, _p]),

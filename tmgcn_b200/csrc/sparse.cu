@@ -7,6 +7,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace tmgcn {
@@ -534,6 +536,29 @@ __global__ void __launch_bounds__(32) merge_rows_staged(const int64_t *__restric
     }
 }
 
+// ---- union-list variant of the tiled transform (default when the caller passes a workspace) ---------------------
+// The count pass already walks the union pattern of every (group of TT output slices) x (32-row block) task; it
+// records it -- column and hit mask of every union entry, iteration-major, plus the per-row union length -- in a
+// fixed-stride workspace record, and the fill pass (fill_from_union) never merges again: it turns the record into
+// values with one LANE per union entry.  Workspace: [header 256 B: int n_overflow_tasks][n_tasks records].
+constexpr size_t UNION_HEADER = 256;
+__host__ __device__ __forceinline__ size_t union_stride(int qc) { return 64 + (size_t)qc * 192; }
+struct UnionTask {
+    int g;
+    int64_t blk;
+};
+__device__ __forceinline__ UnionTask union_task(int64_t task, int64_t nblk, int n_groups, bool block_major) {
+    UnionTask u;
+    if (block_major) {
+        u.blk = task / n_groups;
+        u.g = (int)(task - u.blk * n_groups);
+    } else {
+        u.g = (int)(task / nblk);
+        u.blk = task - (int64_t)u.g * nblk;
+    }
+    return u;
+}
+
 // Time-tiled fill (default for fp32 values, b <= 12, short rows; TMGCN_MERGE_TT=0 disables).  TT = 4 consecutive output slices of the
 // same 32 rows share B-1 of their B source slices, so ONE merge over the NS = B-1+TT sources feeds all four:
 // a step takes the smallest pending column, every cursor sitting on it hands over its value, and output tt
@@ -548,7 +573,8 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                                                        int64_t N, const double *__restrict__ band_w, int b,
                                                        int pool, int64_t *__restrict__ out_counts,
                                                        const int64_t *__restrict__ out_rowptr,
-                                                       int32_t *__restrict__ out_col, float *__restrict__ out_val) {
+                                                       int32_t *__restrict__ out_col, float *__restrict__ out_val,
+                                                       uint8_t *__restrict__ utmp = nullptr, int qc = 0) {
     // COUNT: the plan pass on the same structure -- only the columns are staged (4-byte entries: half the
     // shared memory per warp, twice the resident warps), a step is the min tree + one predicated cursor step per
     // source, and output tt counts a column iff one of its non-zero-weight slots was hit.  ~7x fewer
@@ -563,11 +589,16 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
     const int n_groups = (T_out + TT - 1) / TT;
     const int64_t n_tasks = (int64_t)n_groups * nblk;
     for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const int g = (int)(task / nblk);
+        // union variant (utmp != nullptr): row-block-major task order, so the groups of one row block -- which share
+        // B-1 of their source slices -- run back to back and re-read those segments from L2, not from DRAM
+        const UnionTask ut = union_task(task, nblk, n_groups, COUNT && utmp != nullptr);
+        const int g = ut.g;
         const int t0 = g * TT;
-        const int64_t i = (task - (int64_t)g * nblk) * 32 + lane;
+        const int64_t i = ut.blk * 32 + lane;
         const bool live = i < N;
         const int64_t ic = live ? i : N - 1;
+        // union-list record of this task (see fill_from_union): [ulen: 32 x u16][col: qc x 32 x i32][mask: qc x 32 x u16]
+        uint8_t *const urec = (COUNT && utmp != nullptr) ? utmp + UNION_HEADER + (size_t)task * union_stride(qc) : nullptr;
         // weights of output tt on slot k (lag l = B-1-k+tt), zero outside its window / the band / the tensor
         double w[COUNT ? 1 : TT][COUNT ? 1 : B];
         uint32_t nz[TT];                         // slots whose weight for output tt is non-zero
@@ -660,6 +691,7 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                 else
                     cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], -1, 0.0, unused);
             }
+            int q = 0;                           // union entries of this row so far (= loop iterations)
             while (true) {
                 int m = cur[0];
 #pragma unroll
@@ -672,6 +704,15 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                     const bool hit = cur[k] == m;
                     hits |= hit ? (1u << k) : 0u;
                     if (!COUNT) vd[COUNT ? 0 : k] = hit ? (double)__int_as_float(v[k]) : 0.0;  // +0 leaves a chain unchanged
+                }
+                if (COUNT && urec != nullptr) {
+                    // iteration-major record: the q-th union entry of lane's row at [q][lane] -- the lanes still
+                    // merging write one coalesced line of columns and one of hit masks per iteration
+                    if (q < qc) {
+                        reinterpret_cast<int32_t *>(urec + 64)[q * 32 + lane] = m;
+                        reinterpret_cast<uint16_t *>(urec + 64 + (size_t)qc * 128)[q * 32 + lane] = (uint16_t)hits;
+                    }
+                    ++q;
                 }
 #pragma unroll
                 for (int tt = 0; tt < TT; ++tt) {
@@ -697,7 +738,16 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                         cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
                 }
             }
+            if (COUNT && urec != nullptr) {
+                const bool over = q > qc;        // a row longer than the record: the fill pass re-merges this task
+                reinterpret_cast<uint16_t *>(urec)[lane] = over ? (uint16_t)0xFFFF : (uint16_t)q;
+                if (__any_sync(0xffffffffu, over) && lane == 0) atomicAdd(reinterpret_cast<int *>(utmp), 1);
+            }
         } else {
+            if (COUNT && urec != nullptr) {
+                reinterpret_cast<uint16_t *>(urec)[lane] = (uint16_t)0xFFFF;
+                if (lane == 0) atomicAdd(reinterpret_cast<int *>(utmp), 1);
+            }
             // hub blocks: the same merge on global memory
             int64_t gp[NS], ge[NS];
             int32_t cur[NS];
@@ -757,10 +807,400 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
     }
 }
 
+// Fill pass of the union-list variant.  A warp owns one task (TT output slices x 32 rows).  The task's record
+// gives the union pattern; its entries are walked in row-major order with one LANE per entry.  Because every
+// source slice stores the block's rows back to back and in the same (row, column) order as the union list, the
+// value of source slot k for an entry with hit bit k is at
+//     first entry of the block in that slice + #(earlier union entries with bit k)
+// -- a running count kept per slot plus a ballot/popcount rank inside the chunk: no merge, no compare, and the
+// gathers of a warp are monotone (coalesced).  Output tt then forms ITS fp64 FMA chain over the slots of its window
+// in ascending slice order (absent sources contribute w * (+0): the bits of the merging kernels) and the entries
+// present in tt are written at base_tt + rank: again a ballot/popcount, fully coalesced stores.
+// Tasks whose record overflowed (a row longer than qc, or a block that did not fit the count pass's staging pool)
+// are re-merged from global memory (tiled_task_global): same sums, same order.
+template <int B, int TT, typename VT>
+__device__ __forceinline__ void tiled_task_global(const int64_t *__restrict__ in_rowptr,
+                                                  const int32_t *__restrict__ in_col, const VT *__restrict__ in_val,
+                                                  int T_out, int halo, int64_t N, const double *__restrict__ band_w,
+                                                  int b, int t0, int64_t i, bool live,
+                                                  const int64_t *__restrict__ out_rowptr,
+                                                  int32_t *__restrict__ out_col, VT *__restrict__ out_val) {
+    constexpr int NS = B - 1 + TT;
+    const int64_t ic = live ? i : N - 1;
+    double w[TT][B];
+    uint32_t nz[TT];
+    bool used[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) used[k] = false;
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) {
+        nz[tt] = 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int l = B - 1 - j;
+            const int sl = halo + t0 + tt - l;
+            double wl = 0.0;
+            if (l < b && t0 + tt < T_out && sl >= 0) wl = band_w[(int64_t)(t0 + tt) * b + l];
+            w[tt][j] = wl;
+            if (wl != 0.0) {
+                nz[tt] |= 1u << (tt + j);
+                used[tt + j] = true;
+            }
+        }
+    }
+    int64_t gp[NS], ge[NS];
+    int32_t cur[NS];
+    VT v[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        gp[k] = ge[k] = 0;
+        if (used[k] && live) {
+            const int sl = halo + t0 - (B - 1) + k;
+            gp[k] = in_rowptr[(int64_t)sl * N + ic];
+            ge[k] = in_rowptr[(int64_t)sl * N + ic + 1];
+        }
+        const bool in = gp[k] < ge[k];
+        cur[k] = in ? in_col[gp[k]] : INT_MAX;
+        v[k] = in ? in_val[gp[k]] : (VT)0;
+    }
+    int32_t *oc[TT];
+    VT *ov[TT];
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) {
+        const int64_t ob = (live && t0 + tt < T_out) ? out_rowptr[(int64_t)(t0 + tt) * N + i] : 0;
+        oc[tt] = out_col + ob;
+        ov[tt] = out_val + ob;
+    }
+    while (true) {
+        int m = cur[0];
+#pragma unroll
+        for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
+        if (m == INT_MAX) break;
+        uint32_t hits = 0;
+        double vd[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const bool hit = cur[k] == m;
+            hits |= hit ? (1u << k) : 0u;
+            vd[k] = hit ? (double)v[k] : 0.0;
+            gp[k] += hit ? 1 : 0;
+        }
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < B; ++j) acc = fma(w[tt][j], vd[tt + j], acc);
+            if (hits & nz[tt]) {
+                *oc[tt] = m;
+                *ov[tt] = (VT)acc;
+                ++oc[tt];
+                ++ov[tt];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const bool in = gp[k] < ge[k];
+            cur[k] = in ? in_col[gp[k]] : INT_MAX;
+            v[k] = in ? in_val[gp[k]] : (VT)0;
+        }
+    }
+}
+
+// One source slot of one chunk of the lane-per-entry walk, as straight-line PTX (the compiler's version of the same
+// C spends 14 instructions per slot re-deriving the predicate and re-loading the base pointer; this is 10):
+//   p = (mask has bit K);  bal = ballot(p);  v = p ? in_val[sb + popc(bal & lanes below)] : +0;  sb += popc(bal)
+template <int K>
+__device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint32_t &sb, const float *base, float &v) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        " and.b32 t, %2, %5;\n"
+        " setp.ne.u32 p, t, 0;\n"
+        " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+        " and.b32 r, bal, %3;\n"
+        " popc.b32 r, r;\n"
+        " add.u32 r, r, %1;\n"
+        " mov.f32 %0, 0f00000000;\n"
+        " mad.wide.u32 a, r, 4, %4;\n"
+        " @p ld.global.nc.f32 %0, [a];\n"
+        " popc.b32 t, bal;\n"
+        " add.u32 %1, %1, t;\n}"
+        : "=f"(v), "+r"(sb)
+        : "r"(mask), "r"(lt), "l"(base), "n"(1u << K)
+        : "memory");
+}
+template <int K>
+__device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint32_t &sb, const double *base, double &v) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        " and.b32 t, %2, %5;\n"
+        " setp.ne.u32 p, t, 0;\n"
+        " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+        " and.b32 r, bal, %3;\n"
+        " popc.b32 r, r;\n"
+        " add.u32 r, r, %1;\n"
+        " mov.f64 %0, 0d0000000000000000;\n"
+        " mad.wide.u32 a, r, 8, %4;\n"
+        " @p ld.global.nc.f64 %0, [a];\n"
+        " popc.b32 t, bal;\n"
+        " add.u32 %1, %1, t;\n}"
+        : "=d"(v), "+r"(sb)
+        : "r"(mask), "r"(lt), "l"(base), "n"(1u << K)
+        : "memory");
+}
+// generic-index version (tensors with 2^32 entries or more)
+template <int K, typename VT>
+__device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint64_t &sb, const VT *base, VT &v) {
+    const bool bit = (mask & (1u << K)) != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+    v = (VT)0;
+    if (bit) v = base[sb + (uint64_t)__popc(bal & lt)];
+    sb += (uint64_t)__popc(bal);
+}
+template <typename VT, typename IdxT, int... K>
+__device__ __forceinline__ void gather_slots(std::integer_sequence<int, K...>, uint32_t mask, uint32_t lt,
+                                             IdxT (&sb)[sizeof...(K)], const VT *base, VT (&v)[sizeof...(K)]) {
+    (slot_gather<K>(mask, lt, sb[K], base, v[K]), ...);
+}
+// One output slice of one chunk: entries present in it (mask & nz) are written at ob + rank, ob advances.
+__device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t lt, uint32_t &ob, int32_t *out_col,
+                                          float *out_val, int32_t col, float val) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        " and.b32 t, %1, %2;\n"
+        " setp.ne.u32 p, t, 0;\n"
+        " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+        " and.b32 r, bal, %3;\n"
+        " popc.b32 r, r;\n"
+        " add.u32 r, r, %0;\n"
+        " mad.wide.u32 a, r, 4, %4;\n"
+        " @p st.global.b32 [a], %6;\n"
+        " mad.wide.u32 a, r, 4, %5;\n"
+        " @p st.global.f32 [a], %7;\n"
+        " popc.b32 t, bal;\n"
+        " add.u32 %0, %0, t;\n}"
+        : "+r"(ob)
+        : "r"(mask), "r"(nz), "r"(lt), "l"(out_col), "l"(out_val), "r"(col), "f"(val)
+        : "memory");
+}
+__device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t lt, uint32_t &ob, int32_t *out_col,
+                                          double *out_val, int32_t col, double val) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        " and.b32 t, %1, %2;\n"
+        " setp.ne.u32 p, t, 0;\n"
+        " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+        " and.b32 r, bal, %3;\n"
+        " popc.b32 r, r;\n"
+        " add.u32 r, r, %0;\n"
+        " mad.wide.u32 a, r, 4, %4;\n"
+        " @p st.global.b32 [a], %6;\n"
+        " mad.wide.u32 a, r, 8, %5;\n"
+        " @p st.global.f64 [a], %7;\n"
+        " popc.b32 t, bal;\n"
+        " add.u32 %0, %0, t;\n}"
+        : "+r"(ob)
+        : "r"(mask), "r"(nz), "r"(lt), "l"(out_col), "l"(out_val), "r"(col), "d"(val)
+        : "memory");
+}
+template <typename VT>
+__device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t lt, uint64_t &ob, int32_t *out_col,
+                                          VT *out_val, int32_t col, VT val) {
+    const bool pres = (mask & nz) != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, pres);
+    if (pres) {
+        const uint64_t pos = ob + (uint64_t)__popc(bal & lt);
+        out_col[pos] = col;
+        out_val[pos] = val;
+    }
+    ob += (uint64_t)__popc(bal);
+}
+
+template <int B, int TT, typename VT, typename IdxT>
+__global__ void __launch_bounds__(32) fill_from_union(const int64_t *__restrict__ in_rowptr,
+                                                      const int32_t *__restrict__ in_col,
+                                                      const VT *__restrict__ in_val, int T_out, int halo, int64_t N,
+                                                      const double *__restrict__ band_w, int b,
+                                                      const uint8_t *__restrict__ utmp, int qc,
+                                                      const int64_t *__restrict__ out_rowptr,
+                                                      int32_t *__restrict__ out_col, VT *__restrict__ out_val) {
+    constexpr int NS = B - 1 + TT;
+    static_assert(NS <= 16, "hit masks are 16 bits");
+    extern __shared__ __align__(16) uint8_t stage_raw[];
+    // [col: row-major packed, qc x 32 x i32][mask: row-major packed, qc x 32 x u16][raw masks of the record, qc x 32 x u16]
+    const int32_t *const s_col = reinterpret_cast<const int32_t *>(stage_raw);
+    uint16_t *const s_mask = reinterpret_cast<uint16_t *>(stage_raw + (size_t)qc * 128);
+    const uint16_t *const s_raw = reinterpret_cast<const uint16_t *>(stage_raw + (size_t)qc * 192);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_raw);
+    const int lane = threadIdx.x;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t nblk = (N + 31) / 32;
+    const int n_groups = (T_out + TT - 1) / TT;
+    const int64_t n_tasks = (int64_t)n_groups * nblk;
+    const size_t stride = union_stride(qc);
+    for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const UnionTask ut = union_task(task, nblk, n_groups, true);
+        const int t0 = ut.g * TT;
+        const int64_t r0 = ut.blk * 32;
+        const uint8_t *const urec = utmp + UNION_HEADER + (size_t)task * stride;
+        const uint32_t ul = reinterpret_cast<const uint16_t *>(urec)[lane];
+        if (__any_sync(0xffffffffu, ul == 0xFFFFu)) continue;                 // overflowed record: fill_union_overflow
+        // row offsets of the row-major walk (exclusive scan of the union lengths) and the longest row
+        uint32_t incl = ul;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        const int Ltot = (int)__shfl_sync(0xffffffffu, incl, 31);
+        uint32_t qmax = ul;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) qmax = max(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+        // stage the record TRANSPOSED: the record is iteration-major ([q][row], what the merging lanes could write
+        // coalesced), the walk is row-major.  Columns go straight to their packed place (4-byte copies: lane = row,
+        // a coalesced line per iteration); the 2-byte hit masks are copied raw (16-byte copies) and transposed from
+        // shared memory once they have landed.  Everything is in flight together.
+        const uint32_t roff = incl - ul;
+        {
+            const int32_t *src = reinterpret_cast<const int32_t *>(urec + 64) + lane;
+            uint32_t dst = sbase + roff * 4;
+            for (uint32_t q = 0; q < ul; ++q, src += 32, dst += 4)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            const uint8_t *msrc = urec + 64 + (size_t)qc * 128;
+            const int nm = (int)qmax * 4;                                    // 64 B of hit masks per iteration
+            for (int x = lane; x < nm; x += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)qc * 192 +
+                                                                               (uint32_t)x * 16),
+                             "l"(msrc + (size_t)x * 16)
+                             : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        // weights of output tt on the j-th slot of its window (slot k = tt + j, lag l = B-1-j) -- as merge_rows_tiled
+        double w[TT][B];
+        uint32_t nz[TT];
+        bool used[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) used[k] = false;
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) {
+            nz[tt] = 0;
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const int l = B - 1 - j;
+                const int sl = halo + t0 + tt - l;
+                double wl = 0.0;
+                if (l < b && t0 + tt < T_out && sl >= 0) wl = band_w[(int64_t)(t0 + tt) * b + l];
+                w[tt][j] = wl;
+                if (wl != 0.0) {
+                    nz[tt] |= 1u << (tt + j);
+                    used[tt + j] = true;
+                }
+            }
+        }
+        // running positions: first entry of the block in every source slot, first output entry of the block
+        // (IdxT = uint32_t when both tensors hold fewer than 2^32 entries: one IMAD.WIDE per address)
+        IdxT sb[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            sb[k] = 0;
+            if (used[k]) sb[k] = (IdxT)in_rowptr[(int64_t)(halo + t0 - (B - 1) + k) * N + r0];
+        }
+        IdxT ob[TT];
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) ob[tt] = t0 + tt < T_out ? (IdxT)out_rowptr[(int64_t)(t0 + tt) * N + r0] : 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        for (uint32_t q = 0; q < ul; ++q) s_mask[roff + q] = s_raw[q * 32 + lane];
+        __syncwarp();
+        // The walk is software-pipelined: the front half of chunk c+1 (entry lookup, ranks, the NS gathers) is
+        // issued before the back half of chunk c (fp64 chains, stores), so the gathers' latency hides behind it.
+        struct Front {
+            int32_t col;
+            uint32_t mask;
+            VT v[NS];
+        };
+        auto front = [&](int e0, Front &f) {
+            const int e = e0 + lane;
+            f.col = 0;
+            f.mask = 0;
+            if (e < Ltot) {
+                f.col = s_col[e];
+                f.mask = s_mask[e];
+            }
+            gather_slots<VT, IdxT>(std::make_integer_sequence<int, NS>{}, f.mask, lt, sb, in_val, f.v);
+        };
+        auto back = [&](const Front &f) {
+            double vd[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) vd[k] = (double)f.v[k];            // +0 leaves a chain unchanged
+#pragma unroll
+            for (int tt = 0; tt < TT; ++tt) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < B; ++j) acc = fma(w[tt][j], vd[tt + j], acc);
+                slot_emit(f.mask, nz[tt], lt, ob[tt], out_col, out_val, f.col, (VT)acc);
+            }
+        };
+        Front fa, fb;
+        if (Ltot > 0) front(0, fa);
+        for (int e0 = 0; e0 < Ltot; e0 += 64) {                             // all conditions are warp-uniform
+            const bool more1 = e0 + 32 < Ltot;
+            if (more1) front(e0 + 32, fb);
+            back(fa);
+            if (!more1) break;
+            if (e0 + 64 < Ltot) front(e0 + 64, fa);
+            back(fb);
+        }
+        __syncwarp();                            // the staging buffers are reused by the next task
+    }
+}
+
+// second launch of the union-list fill: the tasks whose record overflowed are merged from global memory (kept out
+// of fill_from_union so that its register allocation is that of the lane-per-entry loop alone)
+template <int B, int TT, typename VT>
+__global__ void __launch_bounds__(128) fill_union_overflow(const int64_t *__restrict__ in_rowptr,
+                                                           const int32_t *__restrict__ in_col,
+                                                           const VT *__restrict__ in_val, int T_out, int halo,
+                                                           int64_t N, const double *__restrict__ band_w, int b,
+                                                           const uint8_t *__restrict__ utmp, int qc,
+                                                           const int64_t *__restrict__ out_rowptr,
+                                                           int32_t *__restrict__ out_col, VT *__restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nblk = (N + 31) / 32;
+    const int n_groups = (T_out + TT - 1) / TT;
+    const int64_t n_tasks = (int64_t)n_groups * nblk;
+    const size_t stride = union_stride(qc);
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t task = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < n_tasks; task += warps_total) {
+        const uint32_t ul = reinterpret_cast<const uint16_t *>(utmp + UNION_HEADER + (size_t)task * stride)[lane];
+        if (!__any_sync(0xffffffffu, ul == 0xFFFFu)) continue;
+        const UnionTask ut = union_task(task, nblk, n_groups, true);
+        const int64_t i = ut.blk * 32 + lane;
+        tiled_task_global<B, TT, VT>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b, ut.g * TT, i, i < N,
+                                     out_rowptr, out_col, out_val);
+        __syncwarp();
+    }
+}
+
+// largest record depth (union entries per row) a workspace of ws_bytes gives the n_tasks tasks; 0 = no union variant
+static int union_qc(const void *ws, size_t ws_bytes, int64_t n_tasks) {
+    if (ws == nullptr || n_tasks <= 0 || ws_bytes <= UNION_HEADER) return 0;
+    const size_t per_task = (ws_bytes - UNION_HEADER) / (size_t)n_tasks;
+    if (per_task < union_stride(8)) return 0;
+    size_t qc = (per_task - 64) / 192;
+    if (qc > 240) qc = 240;
+    return (int)qc;
+}
+
+static bool env_flag(const char *name, bool dflt) {
+    const char *e = getenv(name);
+    if (!e || !e[0]) return dflt;
+    return e[0] != '0';
+}
+
 template <bool COUNT_ONLY, typename VT>
 static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const VT *in_val, int T_out, int halo,
                         int64_t N, const double *band_w, int b, int64_t *out_counts, const int64_t *out_rowptr,
-                        int32_t *out_col, VT *out_val, cudaStream_t st) {
+                        int32_t *out_col, VT *out_val, cudaStream_t st, void *ws = nullptr, size_t ws_bytes = 0) {
     // Count pass: thread per row (cols only: issue-bound at full occupancy, faster than staging).
     // Fill pass: the staged kernel when the rows are short enough for a warp's block to fit its staging
     // buffers -- 1.9x faster on the 2 M-node shard (ncu: 18 GB of DRAM traffic instead of 205 GB for 390 M
@@ -780,6 +1220,7 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
     constexpr size_t entry = COUNT_ONLY ? 8 : StageEntry<COUNT_ONLY, VT>::SIZE;
     int sel = 0;
     int cap = 0;
+    double mean_row = 0.0;                                                  // stored entries per source row
     if (forced != 0) {
         int bb = 2;                                                         // the template width b rounds up to
         for (const int cand : {2, 4, 6, 8, 10, 12, 16, 20, 24, 32})
@@ -800,6 +1241,7 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
             TMGCN_CUDA(cudaMemcpyAsync(&nnz_in, in_rowptr + rows_in, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
             TMGCN_CUDA(cudaStreamSynchronize(st));
             const double mean = rows_in > 0 ? (double)nnz_in / (double)rows_in : 0.0;
+            mean_row = mean;
             for (const int ll : {1, 2}) {                                    // 4 lanes per row only pays when forced
                 const double need = mean * (32 / ll);
                 if (need + 4.0 * sqrt(need) + 16.0 <= (double)cap && ll <= bb) {
@@ -809,32 +1251,96 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
             }
         }
     }
-    if constexpr (sizeof(VT) == 4) {
+    {
         static int tiled = -1;
-        if (tiled < 0) {
-            const char *e = getenv("TMGCN_MERGE_TT");
-            tiled = (e && e[0] == '0') ? 0 : 1;          // default on (TMGCN_MERGE_TT=0 selects the per-slice kernels)
-        }
-        // the tiled kernel pays off when a warp's B-1+4 source segments fit its staging pool (sel >= 1 says the
-        // per-slice staged kernel would fit too); forced variants (TMGCN_MERGE_STAGED) bypass it
+        if (tiled < 0) tiled = env_flag("TMGCN_MERGE_TT", true) ? 1 : 0;   // TMGCN_MERGE_TT=0: the per-slice kernels
+        // the tiled kernels pay off when a warp's B-1+4 source segments fit its staging pool (sel >= 1 says the
+        // per-slice staged kernel would fit too); forced variants (TMGCN_MERGE_STAGED) bypass them
         if (tiled && b <= 12 && forced < 0 && sel >= 1 && T_out >= 4) {
-            const int pool = (38 * 1024) / 8;                               // staged entries ({col, val}; count: col)
-            const size_t smem = (size_t)pool * (COUNT_ONLY ? 4 : 8);
             const int64_t n_tasks = (int64_t)ceil_div(T_out, 4) * ceil_div(N, (int64_t)32);
+            // union-list variant: the count pass records the union pattern in the workspace, the fill pass is
+            // fill_from_union (TMGCN_MERGE_UNION=0 or no workspace: the merging fill kernels)
+            static int union_on = -1;
+            if (union_on < 0) union_on = env_flag("TMGCN_MERGE_UNION", true) ? 1 : 0;
+            const int qc = union_on ? union_qc(ws, ws_bytes, n_tasks) : 0;
+            int pool = (38 * 1024) / 8;                                     // staged entries ({col, val}; count: col)
+            if (COUNT_ONLY && qc) {
+                // Only columns are staged here, so the pool can afford the spread of the block sums: a row's length
+                // persists over the band's source slices, so the sum over a 32-row block of NS slices spreads like
+                // NS * sqrt(32 * mean), not like the square root of the total (4 % of the benchmark's blocks
+                // overflowed the fixed pool and were merged from global memory by both passes).
+                int bb = 2;
+                for (const int cand : {2, 4, 6, 8, 10, 12})
+                    if (b <= cand) {
+                        bb = cand;
+                        break;
+                    }
+                const double ns = bb - 1 + 4, blk = 32.0 * mean_row;
+                int want = ((int)(ns * blk + 3.5 * ns * sqrt(blk) + 64.0) + 15) & ~15;
+                if (want > 12288) want = 12288;
+                if (want > pool) pool = want;
+            }
+            const size_t smem = (size_t)pool * (COUNT_ONLY ? 4 : 8);
             int per_sm = (int)((220 * 1024) / (smem + 1024));
             if (per_sm > 16) per_sm = 16;
             int64_t g = (int64_t)sm_count() * per_sm;
             if (g > n_tasks) g = n_tasks;
+            if (qc) TMGCN_REQUIRE(((uintptr_t)ws & 15) == 0, "mtransform_sparse: workspace must be 16-byte aligned");
+            if (COUNT_ONLY && qc) TMGCN_CUDA(cudaMemsetAsync(ws, 0, UNION_HEADER, st));
+            bool union_fill = false;
+            int n_over = 0;
+            bool idx32 = false;
+            if (!COUNT_ONLY && qc) {
+                int64_t nnz_io[2] = {0, 0};
+                TMGCN_CUDA(cudaMemcpyAsync(&n_over, ws, sizeof(int), cudaMemcpyDeviceToHost, st));
+                TMGCN_CUDA(cudaMemcpyAsync(&nnz_io[0], in_rowptr + (int64_t)(T_out + halo) * N, sizeof(int64_t),
+                                           cudaMemcpyDeviceToHost, st));
+                TMGCN_CUDA(cudaMemcpyAsync(&nnz_io[1], out_rowptr + (int64_t)T_out * N, sizeof(int64_t),
+                                           cudaMemcpyDeviceToHost, st));
+                TMGCN_CUDA(cudaStreamSynchronize(st));
+                union_fill = (int64_t)n_over * 20 <= n_tasks;               // mostly overflowed records: merge again
+                idx32 = nnz_io[0] < ((int64_t)1 << 32) && nnz_io[1] < ((int64_t)1 << 32);
+            }
+#define TMGCN_UNION_FILL(BB)                                                                                     \
+    if (b <= BB) {                                                                                               \
+        auto kern = idx32 ? fill_from_union<BB, 4, VT, uint32_t> : fill_from_union<BB, 4, VT, uint64_t>;         \
+        const size_t usmem = (size_t)qc * 256;                                                                   \
+        TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));         \
+        int occ = 0;                                                                                             \
+        TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, usmem));                        \
+        int64_t ug = (int64_t)sm_count() * (occ > 0 ? occ : 1);                                                  \
+        if (ug > n_tasks) ug = n_tasks;                                                                          \
+        kern<<<(unsigned)ug, 32, usmem, st>>>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b,              \
+                                              (const uint8_t *)ws, qc, out_rowptr, out_col, out_val);            \
+        if (after_launch("fill_from_union")) return 1;                                                           \
+        if (n_over == 0) return 0;                                                                               \
+        int64_t og = ceil_div(n_tasks, (int64_t)4);                                                              \
+        if (og > (int64_t)sm_count() * 8) og = (int64_t)sm_count() * 8;                                          \
+        fill_union_overflow<BB, 4, VT><<<(unsigned)og, 128, 0, st>>>(in_rowptr, in_col, in_val, T_out, halo, N,  \
+                                                                     band_w, b, (const uint8_t *)ws, qc,         \
+                                                                     out_rowptr, out_col, out_val);              \
+        return after_launch("fill_union_overflow");                                                              \
+    }
+            if constexpr (!COUNT_ONLY) {
+                if (union_fill) {
+                    TMGCN_UNION_FILL(2) TMGCN_UNION_FILL(4) TMGCN_UNION_FILL(6) TMGCN_UNION_FILL(8) TMGCN_UNION_FILL(10)
+                    TMGCN_UNION_FILL(12)
+                }
+            }
+#undef TMGCN_UNION_FILL
+            if constexpr (sizeof(VT) == 4) {
 #define TMGCN_TILED(BB)                                                                                          \
     if (b <= BB) {                                                                                               \
         auto kern = merge_rows_tiled<BB, 4, COUNT_ONLY>;                                                         \
         TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
         kern<<<(unsigned)g, 32, smem, st>>>(in_rowptr, in_col, (const float *)in_val, T_out, halo, N, band_w, b, \
-                                            pool, out_counts, out_rowptr, out_col, (float *)out_val);            \
+                                            pool, out_counts, out_rowptr, out_col, (float *)out_val,             \
+                                            (COUNT_ONLY && qc) ? (uint8_t *)ws : nullptr, qc);                   \
         return after_launch(COUNT_ONLY ? "merge_rows_tiled<count>" : "merge_rows_tiled<fill>");                  \
     }
-            TMGCN_TILED(2) TMGCN_TILED(4) TMGCN_TILED(6) TMGCN_TILED(8) TMGCN_TILED(10) TMGCN_TILED(12)
+                TMGCN_TILED(2) TMGCN_TILED(4) TMGCN_TILED(6) TMGCN_TILED(8) TMGCN_TILED(10) TMGCN_TILED(12)
 #undef TMGCN_TILED
+            }
         }
     }
 #define TMGCN_MERGE_STAGED(BB, LL)                                                                               \
@@ -1059,26 +1565,58 @@ static int check_band(int T_out, int halo, int64_t N, int b) {
     return 0;
 }
 
-int tmgcn_mtransform_sparse_plan(const int64_t *in_rowptr, const int32_t *in_col, int T_out, int halo, int64_t N,
-                                 const double *band_w, int b, int64_t *out_counts, void *stream) {
+size_t tmgcn_mtransform_sparse_ws_bytes(int T_out, int halo, int64_t N, int b, int64_t in_nnz) {
+    // record depth: union rows of persistent dynamic graphs run to ~2-3x the mean source row (the band's sources
+    // overlap); deeper rows overflow their record and are re-merged by the fill pass.  0 = variant not applicable.
+    if (T_out < 4 || N <= 0 || b < 1 || b > 12 || halo < 0 || in_nnz <= 0) return 0;
+    if (!env_flag("TMGCN_MERGE_UNION", true) || !env_flag("TMGCN_MERGE_TT", true)) return 0;
+    const double rows_in = (double)(T_out + halo) * (double)N;
+    const double mean = (double)in_nnz / rows_in;
+    int qc = ((int)(mean * 5.0) + 8 + 3) & ~3;
+    if (qc < 16) qc = 16;
+    if (qc > 96) qc = 96;
+    const int64_t n_tasks = ceil_div(T_out, 4) * ceil_div(N, (int64_t)32);
+    const size_t budget = (size_t)16 << 30;
+    while (qc >= 16 && UNION_HEADER + (size_t)n_tasks * union_stride(qc) > budget) qc -= 4;
+    if (qc < 16 || (double)qc < 1.5 * mean) return 0;
+    return UNION_HEADER + (size_t)n_tasks * union_stride(qc);
+}
+
+int tmgcn_mtransform_sparse_plan_ws(const int64_t *in_rowptr, const int32_t *in_col, int T_out, int halo, int64_t N,
+                                    const double *band_w, int b, int64_t *out_counts, void *ws, size_t ws_bytes,
+                                    void *stream) {
     if (check_band(T_out, halo, N, b)) return 1;
     if ((int64_t)T_out * N == 0) return 0;
     TMGCN_REQUIRE(in_rowptr && band_w && out_counts, "mtransform_sparse_plan: null pointer");
     return launch_merge<true, float>(in_rowptr, in_col, nullptr, T_out, halo, N, band_w, b, out_counts, nullptr,
-                                     nullptr, nullptr, (cudaStream_t)stream);
+                                     nullptr, nullptr, (cudaStream_t)stream, ws, ws_bytes);
 }
 
-int tmgcn_mtransform_sparse_run(const int64_t *in_rowptr, const int32_t *in_col, const void *in_val, int T_out,
-                                int halo, int64_t N, const double *band_w, int b, const int64_t *out_rowptr,
-                                int32_t *out_col, void *out_val, int val_is_f64, void *stream) {
+int tmgcn_mtransform_sparse_run_ws(const int64_t *in_rowptr, const int32_t *in_col, const void *in_val, int T_out,
+                                   int halo, int64_t N, const double *band_w, int b, const int64_t *out_rowptr,
+                                   int32_t *out_col, void *out_val, int val_is_f64, void *ws, size_t ws_bytes,
+                                   void *stream) {
     if (check_band(T_out, halo, N, b)) return 1;
     if ((int64_t)T_out * N == 0) return 0;
     TMGCN_REQUIRE(in_rowptr && band_w && out_rowptr, "mtransform_sparse_run: null pointer");
     if (val_is_f64)
         return launch_merge<false, double>(in_rowptr, in_col, (const double *)in_val, T_out, halo, N, band_w, b,
-                                           nullptr, out_rowptr, out_col, (double *)out_val, (cudaStream_t)stream);
+                                           nullptr, out_rowptr, out_col, (double *)out_val, (cudaStream_t)stream, ws,
+                                           ws_bytes);
     return launch_merge<false, float>(in_rowptr, in_col, (const float *)in_val, T_out, halo, N, band_w, b, nullptr,
-                                      out_rowptr, out_col, (float *)out_val, (cudaStream_t)stream);
+                                      out_rowptr, out_col, (float *)out_val, (cudaStream_t)stream, ws, ws_bytes);
+}
+
+int tmgcn_mtransform_sparse_plan(const int64_t *in_rowptr, const int32_t *in_col, int T_out, int halo, int64_t N,
+                                 const double *band_w, int b, int64_t *out_counts, void *stream) {
+    return tmgcn_mtransform_sparse_plan_ws(in_rowptr, in_col, T_out, halo, N, band_w, b, out_counts, nullptr, 0, stream);
+}
+
+int tmgcn_mtransform_sparse_run(const int64_t *in_rowptr, const int32_t *in_col, const void *in_val, int T_out,
+                                int halo, int64_t N, const double *band_w, int b, const int64_t *out_rowptr,
+                                int32_t *out_col, void *out_val, int val_is_f64, void *stream) {
+    return tmgcn_mtransform_sparse_run_ws(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b, out_rowptr, out_col,
+                                          out_val, val_is_f64, nullptr, 0, stream);
 }
 
 int tmgcn_csr_axpby_plan(const int64_t *a_rowptr, const int32_t *a_col, const int64_t *b_rowptr, const int32_t *b_col,

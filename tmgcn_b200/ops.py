@@ -273,15 +273,24 @@ def mtransform_sparse(csr: SliceCSR, band: Band, t0: int = 0, t1: Optional[int] 
     N = csr.N
     dev = csr.rowptr.device
     counts = torch.empty(T_out * N, dtype=torch.int64, device=dev)
-    _lib.check(lib.tmgcn_mtransform_sparse_plan(_p(csr.rowptr), _p(csr.col), T_out, halo, N, _p(w), band.b,
-                                                _p(counts), _stream()))
+    # workspace of the union-list variant (0 bytes = not applicable: the fill pass merges again)
+    ws_bytes = int(lib.tmgcn_mtransform_sparse_ws_bytes(T_out, halo, N, band.b, csr.nnz))
+    ws = None
+    if ws_bytes:
+        try:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        except torch.cuda.OutOfMemoryError:
+            ws_bytes = 0
+    _lib.check(lib.tmgcn_mtransform_sparse_plan_ws(_p(csr.rowptr), _p(csr.col), T_out, halo, N, _p(w), band.b,
+                                                   _p(counts), _p(ws), ws_bytes, _stream()))
     rowptr = exclusive_scan(counts)
     del counts
     nnz = int(rowptr[-1].item())
     col = torch.empty(nnz, dtype=torch.int32, device=dev)
     val = torch.empty(nnz, dtype=csr.val.dtype, device=dev)
-    _lib.check(lib.tmgcn_mtransform_sparse_run(_p(csr.rowptr), _p(csr.col), _p(csr.val), T_out, halo, N, _p(w),
-                                               band.b, _p(rowptr), _p(col), _p(val), 1 if f64 else 0, _stream()))
+    _lib.check(lib.tmgcn_mtransform_sparse_run_ws(_p(csr.rowptr), _p(csr.col), _p(csr.val), T_out, halo, N, _p(w),
+                                                  band.b, _p(rowptr), _p(col), _p(val), 1 if f64 else 0,
+                                                  _p(ws), ws_bytes, _stream()))
     return SliceCSR(T_out, N, rowptr, col, val)
 
 
