@@ -573,8 +573,7 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                                                        int64_t N, const double *__restrict__ band_w, int b,
                                                        int pool, int64_t *__restrict__ out_counts,
                                                        const int64_t *__restrict__ out_rowptr,
-                                                       int32_t *__restrict__ out_col, float *__restrict__ out_val,
-                                                       uint8_t *__restrict__ utmp = nullptr, int qc = 0) {
+                                                       int32_t *__restrict__ out_col, float *__restrict__ out_val) {
     // COUNT: the plan pass on the same structure -- only the columns are staged (4-byte entries: half the
     // shared memory per warp, twice the resident warps), a step is the min tree + one predicated cursor step per
     // source, and output tt counts a column iff one of its non-zero-weight slots was hit.  ~7x fewer
@@ -589,16 +588,11 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
     const int n_groups = (T_out + TT - 1) / TT;
     const int64_t n_tasks = (int64_t)n_groups * nblk;
     for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        // union variant (utmp != nullptr): row-block-major task order, so the groups of one row block -- which share
-        // B-1 of their source slices -- run back to back and re-read those segments from L2, not from DRAM
-        const UnionTask ut = union_task(task, nblk, n_groups, COUNT && utmp != nullptr);
-        const int g = ut.g;
+        const int g = (int)(task / nblk);
         const int t0 = g * TT;
-        const int64_t i = ut.blk * 32 + lane;
+        const int64_t i = (task - (int64_t)g * nblk) * 32 + lane;
         const bool live = i < N;
         const int64_t ic = live ? i : N - 1;
-        // union-list record of this task (see fill_from_union): [ulen: 32 x u16][col: qc x 32 x i32][mask: qc x 32 x u16]
-        uint8_t *const urec = (COUNT && utmp != nullptr) ? utmp + UNION_HEADER + (size_t)task * union_stride(qc) : nullptr;
         // weights of output tt on slot k (lag l = B-1-k+tt), zero outside its window / the band / the tensor
         double w[COUNT ? 1 : TT][COUNT ? 1 : B];
         uint32_t nz[TT];                         // slots whose weight for output tt is non-zero
@@ -691,7 +685,6 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                 else
                     cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], -1, 0.0, unused);
             }
-            int q = 0;                           // union entries of this row so far (= loop iterations)
             while (true) {
                 int m = cur[0];
 #pragma unroll
@@ -704,15 +697,6 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                     const bool hit = cur[k] == m;
                     hits |= hit ? (1u << k) : 0u;
                     if (!COUNT) vd[COUNT ? 0 : k] = hit ? (double)__int_as_float(v[k]) : 0.0;  // +0 leaves a chain unchanged
-                }
-                if (COUNT && urec != nullptr) {
-                    // iteration-major record: the q-th union entry of lane's row at [q][lane] -- the lanes still
-                    // merging write one coalesced line of columns and one of hit masks per iteration
-                    if (q < qc) {
-                        reinterpret_cast<int32_t *>(urec + 64)[q * 32 + lane] = m;
-                        reinterpret_cast<uint16_t *>(urec + 64 + (size_t)qc * 128)[q * 32 + lane] = (uint16_t)hits;
-                    }
-                    ++q;
                 }
 #pragma unroll
                 for (int tt = 0; tt < TT; ++tt) {
@@ -738,16 +722,7 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
                         cursor_step<false, float, false>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
                 }
             }
-            if (COUNT && urec != nullptr) {
-                const bool over = q > qc;        // a row longer than the record: the fill pass re-merges this task
-                reinterpret_cast<uint16_t *>(urec)[lane] = over ? (uint16_t)0xFFFF : (uint16_t)q;
-                if (__any_sync(0xffffffffu, over) && lane == 0) atomicAdd(reinterpret_cast<int *>(utmp), 1);
-            }
         } else {
-            if (COUNT && urec != nullptr) {
-                reinterpret_cast<uint16_t *>(urec)[lane] = (uint16_t)0xFFFF;
-                if (lane == 0) atomicAdd(reinterpret_cast<int *>(utmp), 1);
-            }
             // hub blocks: the same merge on global memory
             int64_t gp[NS], ge[NS];
             int32_t cur[NS];
@@ -803,6 +778,220 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
             for (int tt = 0; tt < TT; ++tt)
                 if (live && t0 + tt < T_out) out_counts[(int64_t)(t0 + tt) * N + i] = cnt[tt];
         }
+        __syncwarp();                            // the pool is reused by the next task
+    }
+}
+
+// Count pass of the union-list variant: merge_rows_tiled<COUNT> plus the record, restructured around what its
+// profile showed (ncu, benchmark shard: 6.2 K warp-instructions per task, of which the merge loop was 3.6 K):
+//   * a CTA keeps ONE group of output slices and walks the row blocks (grid = n_groups x walkers), so the band
+//     weights' non-zero pattern is derived once per CTA, not per task; the CTAs of the groups of one row block run
+//     side by side and share its source segments through L2;
+//   * the source segments are staged by the copy engine: one elected lane issues a 1-D bulk copy
+//     (cp.async.bulk, mbarrier completion) per segment over the enclosing 16-byte-aligned range, instead of ~140
+//     4-byte cp.async per lane;
+//   * every merge iteration appends the union entry -- column and 16-bit hit mask -- to the task's record,
+//     iteration-major ([q][lane]: the lanes still merging write one coalesced line each).
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    for (int spin = 0; spin < (1 << 26); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();                                    // a lost copy must fail the launch, not hang the device
+}
+
+template <int B, int TT>
+__global__ void __launch_bounds__(32) count_union(const int64_t *__restrict__ in_rowptr,
+                                                  const int32_t *__restrict__ in_col, int64_t in_nnz, int T_out,
+                                                  int halo, int64_t N, const double *__restrict__ band_w, int b,
+                                                  int pool, int64_t *__restrict__ out_counts,
+                                                  uint8_t *__restrict__ utmp, int qc) {
+    constexpr int NS = B - 1 + TT;
+    static_assert(NS <= 16, "hit masks are 16 bits");
+    extern __shared__ __align__(16) uint8_t stage_raw[];
+    uint64_t *const bar = reinterpret_cast<uint64_t *>(stage_raw);          // 16 bytes reserved in front of the pool
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_raw) + 16;   // `pool` column entries
+    const int lane = threadIdx.x;
+    const int64_t nblk = (N + 31) / 32;
+    const int n_groups = (T_out + TT - 1) / TT;
+    const int g = (int)(blockIdx.x % (unsigned)n_groups);
+    const int64_t walker = blockIdx.x / (unsigned)n_groups, n_walkers = gridDim.x / (unsigned)n_groups;
+    const int t0 = g * TT;
+    const size_t stride = union_stride(qc);
+    const int64_t nnz4 = in_nnz & ~(int64_t)3;                              // bulk copies stop at the last whole quad
+    // slots with a non-zero weight for output tt (slot k = tt + j holds lag l = B-1-j), once per CTA
+    uint32_t nz[TT];
+    uint32_t used_bits = 0;
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) {
+        nz[tt] = 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int l = B - 1 - j;
+            const int sl = halo + t0 + tt - l;
+            double wl = 0.0;
+            if (l < b && t0 + tt < T_out && sl >= 0) wl = band_w[(int64_t)(t0 + tt) * b + l];
+            if (wl != 0.0) nz[tt] |= 1u << (tt + j);
+        }
+        used_bits |= nz[tt];
+    }
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    for (int64_t blk = walker; blk < nblk; blk += n_walkers) {
+        const int64_t task = blk * n_groups + g;
+        const int64_t i = blk * 32 + lane;
+        const bool live = i < N;
+        const int64_t ic = live ? i : N - 1;
+        uint8_t *const urec = utmp + UNION_HEADER + (size_t)task * stride;
+        // row pointers of the used slots
+        int64_t p0s[NS], p1s[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            p0s[k] = p1s[k] = 0;
+            if (used_bits & (1u << k)) {         // warp-uniform
+                const int sl = halo + t0 - (B - 1) + k;
+                p0s[k] = in_rowptr[(int64_t)sl * N + ic];
+                p1s[k] = in_rowptr[(int64_t)sl * N + ic + 1];
+            }
+            if (!live) p0s[k] = p1s[k];
+        }
+        // segment k of the block = [seg0, seg1) of in_col; it is staged as the enclosing aligned range [a0, a1)
+        // at pool offset soff[k] (a multiple of 4 entries), so source and destination are 16-byte aligned
+        int64_t a0s[NS];
+        int32_t soff[NS + 1], nbulk[NS], tail0[NS], ntail[NS];
+        soff[0] = 0;
+        uint32_t total_bytes = 0;
+        bool fits = true;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const int64_t seg0 = __shfl_sync(0xffffffffu, p0s[k], 0);
+            const int64_t seg1 = __shfl_sync(0xffffffffu, p1s[k], 31);
+            const int64_t a0 = seg0 & ~(int64_t)3;
+            const int64_t a1 = (seg1 + 3) & ~(int64_t)3;
+            const int64_t span = a1 - a0;
+            a0s[k] = a0;
+            fits = fits && span <= (int64_t)pool;
+            const int64_t bulk_end = a1 < nnz4 ? a1 : nnz4;                 // entries [bulk_end, seg1) go by plain loads
+            const int64_t nb = bulk_end > a0 ? bulk_end - a0 : 0;
+            nbulk[k] = seg1 > seg0 ? (int32_t)(nb > (int64_t)pool ? pool : nb) : 0;
+            const int64_t ts = seg0 > nnz4 ? seg0 : nnz4;
+            tail0[k] = (int32_t)(ts - a0 > (int64_t)pool ? pool : ts - a0);
+            ntail[k] = seg1 > ts ? (int32_t)(seg1 - ts) : 0;                // at most 3
+            soff[k + 1] = soff[k] + (int32_t)(span > (int64_t)pool ? pool + 4 : span);
+            total_bytes += (uint32_t)nbulk[k] * 4u;
+        }
+        fits = fits && soff[NS] <= pool;         // warp-uniform
+        if (fits) {
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(bar)),
+                             "r"(total_bytes)
+                             : "memory");
+#pragma unroll
+                for (int k = 0; k < NS; ++k)
+                    if (nbulk[k] > 0)
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                sbase + (uint32_t)soff[k] * 4u),
+                            "l"(in_col + a0s[k]), "r"((uint32_t)nbulk[k] * 4u),
+                            "r"((uint32_t)__cvta_generic_to_shared(bar))
+                            : "memory");
+            }
+            // the last partial quad of the whole column array (only the final segment can reach it)
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (lane < ntail[k])
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + (uint32_t)(soff[k] + tail0[k] + lane) * 4u),
+                                 "r"(in_col[a0s[k] + tail0[k] + lane])
+                                 : "memory");
+            mbar_wait_bounded(bar, phase);
+            phase ^= 1u;
+        }
+        __syncwarp();
+        int64_t cnt[TT];
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) cnt[tt] = 0;
+        int32_t *const rcol = reinterpret_cast<int32_t *>(urec + 64) + lane;
+        uint16_t *const rmask = reinterpret_cast<uint16_t *>(urec + 64 + (size_t)qc * 128) + lane;
+        int q = 0;                               // union entries of this lane's row so far
+        if (fits) {
+            uint32_t p[NS], e[NS];
+            int32_t cur[NS];
+            int32_t v[NS];
+            double unused = 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                p[k] = sbase + (uint32_t)(soff[k] + (int32_t)(p0s[k] - a0s[k])) * 4u;
+                e[k] = p[k] + (uint32_t)(p1s[k] - p0s[k]) * 4u;
+                v[k] = 0;
+                cur[k] = -2;
+                cursor_step<true, float>(cur[k], v[k], p[k], e[k], -1, 0.0, unused);
+            }
+            while (true) {
+                int m = cur[0];
+#pragma unroll
+                for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
+                if (m == INT_MAX) break;
+                uint32_t hits = 0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) hits |= (cur[k] == m) ? (1u << k) : 0u;
+                if (q < qc) {
+                    rcol[q * 32] = m;
+                    rmask[q * 32] = (uint16_t)hits;
+                }
+                ++q;
+#pragma unroll
+                for (int tt = 0; tt < TT; ++tt) cnt[tt] += (hits & nz[tt]) ? 1 : 0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) cursor_step<true, float>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
+            }
+        } else {
+            // hub blocks: the same merge on global memory; their record is marked overflowed below
+            int64_t gp[NS], ge[NS];
+            int32_t cur[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                gp[k] = p0s[k];
+                ge[k] = p1s[k];
+                cur[k] = gp[k] < ge[k] ? in_col[gp[k]] : INT_MAX;
+            }
+            while (true) {
+                int m = cur[0];
+#pragma unroll
+                for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
+                if (m == INT_MAX) break;
+                uint32_t hits = 0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const bool hit = cur[k] == m;
+                    hits |= hit ? (1u << k) : 0u;
+                    gp[k] += hit ? 1 : 0;
+                }
+#pragma unroll
+                for (int tt = 0; tt < TT; ++tt) cnt[tt] += (hits & nz[tt]) ? 1 : 0;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) cur[k] = gp[k] < ge[k] ? in_col[gp[k]] : INT_MAX;
+            }
+            q = qc + 1;
+        }
+        {
+            const bool over = q > qc;            // a row longer than the record (or a hub block): fill_union_overflow
+            reinterpret_cast<uint16_t *>(urec)[lane] = over ? (uint16_t)0xFFFF : (uint16_t)q;
+            if (__any_sync(0xffffffffu, over) && lane == 0) atomicAdd(reinterpret_cast<int *>(utmp), 1);
+        }
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt)
+            if (live && t0 + tt < T_out) out_counts[(int64_t)(t0 + tt) * N + i] = cnt[tt];
         __syncwarp();                            // the pool is reused by the next task
     }
 }
@@ -1221,6 +1410,7 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
     int sel = 0;
     int cap = 0;
     double mean_row = 0.0;                                                  // stored entries per source row
+    int64_t nnz_in_host = -1;
     if (forced != 0) {
         int bb = 2;                                                         // the template width b rounds up to
         for (const int cand : {2, 4, 6, 8, 10, 12, 16, 20, 24, 32})
@@ -1242,6 +1432,7 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
             TMGCN_CUDA(cudaStreamSynchronize(st));
             const double mean = rows_in > 0 ? (double)nnz_in / (double)rows_in : 0.0;
             mean_row = mean;
+            nnz_in_host = nnz_in;
             for (const int ll : {1, 2}) {                                    // 4 lanes per row only pays when forced
                 const double need = mean * (32 / ll);
                 if (need + 4.0 * sqrt(need) + 16.0 <= (double)cap && ll <= bb) {
@@ -1262,7 +1453,8 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
             // fill_from_union (TMGCN_MERGE_UNION=0 or no workspace: the merging fill kernels)
             static int union_on = -1;
             if (union_on < 0) union_on = env_flag("TMGCN_MERGE_UNION", true) ? 1 : 0;
-            const int qc = union_on ? union_qc(ws, ws_bytes, n_tasks) : 0;
+            int qc = union_on ? union_qc(ws, ws_bytes, n_tasks) : 0;
+            if (((uintptr_t)in_col & 15) != 0 || nnz_in_host < 0) qc = 0;     // the bulk copies need an aligned column array
             int pool = (38 * 1024) / 8;                                     // staged entries ({col, val}; count: col)
             if (COUNT_ONLY && qc) {
                 // Only columns are staged here, so the pool can afford the spread of the block sums: a row's length
@@ -1285,6 +1477,26 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
             if (per_sm > 16) per_sm = 16;
             int64_t g = (int64_t)sm_count() * per_sm;
             if (g > n_tasks) g = n_tasks;
+#define TMGCN_UNION_COUNT(BB)                                                                                    \
+    if (b <= BB) {                                                                                               \
+        auto kern = count_union<BB, 4>;                                                                          \
+        const size_t csmem = smem + 16;                                                                          \
+        TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));         \
+        const int64_t n_groups = ceil_div(T_out, 4), n_blk = ceil_div(N, (int64_t)32);                           \
+        int64_t walkers = ((int64_t)sm_count() * per_sm) / n_groups;                                             \
+        if (walkers < 1) walkers = 1;                                                                            \
+        if (walkers > n_blk) walkers = n_blk;                                                                    \
+        kern<<<(unsigned)(n_groups * walkers), 32, csmem, st>>>(in_rowptr, in_col, nnz_in_host, T_out, halo, N,  \
+                                                                band_w, b, pool, out_counts, (uint8_t *)ws, qc); \
+        return after_launch("count_union");                                                                      \
+    }
+            if constexpr (COUNT_ONLY) {
+                if (qc) {
+                    TMGCN_UNION_COUNT(2) TMGCN_UNION_COUNT(4) TMGCN_UNION_COUNT(6) TMGCN_UNION_COUNT(8)
+                    TMGCN_UNION_COUNT(10) TMGCN_UNION_COUNT(12)
+                }
+            }
+#undef TMGCN_UNION_COUNT
             if (qc) TMGCN_REQUIRE(((uintptr_t)ws & 15) == 0, "mtransform_sparse: workspace must be 16-byte aligned");
             if (COUNT_ONLY && qc) TMGCN_CUDA(cudaMemsetAsync(ws, 0, UNION_HEADER, st));
             bool union_fill = false;
@@ -1334,8 +1546,7 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
         auto kern = merge_rows_tiled<BB, 4, COUNT_ONLY>;                                                         \
         TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
         kern<<<(unsigned)g, 32, smem, st>>>(in_rowptr, in_col, (const float *)in_val, T_out, halo, N, band_w, b, \
-                                            pool, out_counts, out_rowptr, out_col, (float *)out_val,             \
-                                            (COUNT_ONLY && qc) ? (uint8_t *)ws : nullptr, qc);                   \
+                                            pool, out_counts, out_rowptr, out_col, (float *)out_val);            \
         return after_launch(COUNT_ONLY ? "merge_rows_tiled<count>" : "merge_rows_tiled<fill>");                  \
     }
                 TMGCN_TILED(2) TMGCN_TILED(4) TMGCN_TILED(6) TMGCN_TILED(8) TMGCN_TILED(10) TMGCN_TILED(12)
