@@ -621,9 +621,10 @@ def run_workload(wl, ctx, steps, warmup, full):
     if t_tr is not None:
         res["mtransform_sparse"] = {"seconds": t_tr, "transform_edges_per_s": At.nnz / t_tr,
                                     "algorithmic_bytes": tr_bytes, "GB/s": tr_bytes / t_tr / 1e9,
-                                    "note": "stage (a), rank-0 shard: count pass + scan + fill passes, best of two warm "
-                                            "runs, CUDA events (includes the host read of the output size); "
-                                            "bit-identical to the cold run"}
+                                    "note": "stage (a), rank-0 shard: count pass (records the union pattern) + scan + "
+                                            "union-list fill pass, best of two warm runs, CUDA events (includes the "
+                                            "workspace allocation and the host reads of the output size and of the "
+                                            "overflow counter); bit-identical to the cold run"}
     res["T_own"] = T_own
     # release everything before the next workload
     del step, At, plan, H, peer, comm, dOut, W, U

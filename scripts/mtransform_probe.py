@@ -91,7 +91,7 @@ def main():
             runs[name] = {"error": r.stderr[-2000:]}
         else:
             runs[name] = json.loads(r.stdout.strip().splitlines()[-1])
-    same = ("checksum" in runs["union_fill"] and runs["union_fill"].get("checksum") == runs["merging_fill"].get("checksum"))
+    same = all("checksum" in r and r.get("checksum") == runs["merging_fill"].get("checksum") for r in runs.values())
     print(json.dumps({"workload": vars(a), "identical_bits": same, **runs}))
 
 

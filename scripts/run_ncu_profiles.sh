@@ -2,7 +2,7 @@
 # GPU call (1 GPU): ncu launch list + DRAM traffic of the default bench step, one --set full capture of every kernel.
 # The .ncu-rep stays on the box (it is larger than what gpurun copies back); CSV exports come home.
 mkdir -p gpurun_out
-KREG='regex:spmm_|stencil_|gemm_|merge_|readout_|factor_|row_class|scan_|rowptr_|transpose_|sgemm|dw_|reduce_partials|act_|flat_ids|csr_|solve_|gather_'
+KREG='regex:spmm_|stencil_|gemm_|merge_|count_union|fill_from_union|fill_union|readout_|factor_|row_class|scan_|rowptr_|transpose_|sgemm|dw_|reduce_partials|act_|flat_ids|csr_|solve_|gather_'
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$KREG" -c 400 \
     --csv --log-file gpurun_out/r02_launches.csv python bench.py --lean --steps 2 --warmup 3 \
     > gpurun_out/r02_bench_under_ncu.json 2> gpurun_out/r02_bench_under_ncu.err; echo "ncu launches rc=$?"

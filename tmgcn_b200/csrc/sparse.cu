@@ -792,6 +792,30 @@ __global__ void __launch_bounds__(32) merge_rows_tiled(const int64_t *__restrict
 //     4-byte cp.async per lane;
 //   * every merge iteration appends the union entry -- column and 16-bit hit mask -- to the task's record,
 //     iteration-major ([q][lane]: the lanes still merging write one coalesced line each).
+// Count-pass cursor step that also records the hit.  The merge loop is bound by the half-rate integer ALU pipe
+// (ncu: alu 65 %, fma 13 %), so the two predicated updates -- cursor += 4, hits |= bit -- are written as
+// multiply-adds with a run-time 1 (`unit`): ptxas cannot fold them into adds and issues them on the FMA pipe.
+template <int K>
+__device__ __forceinline__ void cursor_step_hits(int32_t &c, uint32_t &p, uint32_t e, int mm, uint32_t &hits,
+                                                 uint32_t unit) {
+    asm volatile(
+        "{\n .reg .pred h, q;\n"
+        " setp.eq.s32 h, %0, %4;\n"
+        " @h mad.lo.u32 %1, %5, 4, %1;\n"
+        " @h mad.lo.u32 %2, %5, %6, %2;\n"
+        " setp.lt.u32 q, %1, %3;\n"
+        " mov.b32 %0, 0x7fffffff;\n"
+        " @q ld.shared.b32 %0, [%1];\n}"
+        : "+r"(c), "+r"(p), "+r"(hits)
+        : "r"(e), "r"(mm), "r"(unit), "n"(1u << K));
+}
+template <int... K>
+__device__ __forceinline__ void cursor_steps_hits(std::integer_sequence<int, K...>, int32_t (&c)[sizeof...(K)],
+                                                  uint32_t (&p)[sizeof...(K)], const uint32_t (&e)[sizeof...(K)],
+                                                  int mm, uint32_t &hits, uint32_t unit) {
+    (cursor_step_hits<K>(c[K], p[K], e[K], mm, hits, unit), ...);
+}
+
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
     for (int spin = 0; spin < (1 << 26); ++spin) {
@@ -807,7 +831,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 }
 
 template <int B, int TT>
-__global__ void __launch_bounds__(32) count_union(const int64_t *__restrict__ in_rowptr,
+__global__ void __launch_bounds__(32, 10) count_union(const int64_t *__restrict__ in_rowptr,
                                                   const int32_t *__restrict__ in_col, int64_t in_nnz, int T_out,
                                                   int halo, int64_t N, const double *__restrict__ band_w, int b,
                                                   int pool, int64_t *__restrict__ out_counts,
@@ -825,6 +849,7 @@ __global__ void __launch_bounds__(32) count_union(const int64_t *__restrict__ in
     const int t0 = g * TT;
     const size_t stride = union_stride(qc);
     const int64_t nnz4 = in_nnz & ~(int64_t)3;                              // bulk copies stop at the last whole quad
+    const uint32_t unit = qc > 0 ? 1u : 0u;                                 // a 1 the compiler cannot see (cursor_step_hits)
     // slots with a non-zero weight for output tt (slot k = tt + j holds lag l = B-1-j), once per CTA
     uint32_t nz[TT];
     uint32_t used_bits = 0;
@@ -943,8 +968,7 @@ __global__ void __launch_bounds__(32) count_union(const int64_t *__restrict__ in
                 for (int k = 1; k < NS; ++k) m = min(m, cur[k]);
                 if (m == INT_MAX) break;
                 uint32_t hits = 0;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) hits |= (cur[k] == m) ? (1u << k) : 0u;
+                cursor_steps_hits(std::make_integer_sequence<int, NS>{}, cur, p, e, m, hits, unit);
                 if (q < qc) {
                     rcol[q * 32] = m;
                     rmask[q * 32] = (uint16_t)hits;
@@ -952,8 +976,6 @@ __global__ void __launch_bounds__(32) count_union(const int64_t *__restrict__ in
                 ++q;
 #pragma unroll
                 for (int tt = 0; tt < TT; ++tt) cnt[tt] += (hits & nz[tt]) ? 1 : 0;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) cursor_step<true, float>(cur[k], v[k], p[k], e[k], m, 0.0, unused);
             }
         } else {
             // hub blocks: the same merge on global memory; their record is marked overflowed below
@@ -1096,22 +1118,28 @@ __device__ __forceinline__ void tiled_task_global(const int64_t *__restrict__ in
 }
 
 // One source slot of one chunk of the lane-per-entry walk, as straight-line PTX (the compiler's version of the same
-// C spends 14 instructions per slot re-deriving the predicate and re-loading the base pointer; this is 10):
-//   p = (mask has bit K);  bal = ballot(p);  v = p ? in_val[sb + popc(bal & lanes below)] : +0;  sb += popc(bal)
+// C spends 14 instructions per slot re-deriving the predicate and re-loading the base pointer):
+//   p = (mask has bit K);  bal = ballot(p);  v = p ? in_val[sb + popc(bal & lanes below)] : +0;
+//   sb += total of the ballot, taken as (rank + own bit) of the last lane by a shuffle: the quarter-rate XU pipe
+//   (popc, cvt) is the busiest pipe of this kernel (ncu: 57 %), so the second popcount is avoided.
+// (A cp.async variant that parks the gathered values in shared memory -- commit groups instead of the register
+// scoreboards, which alias between the two chunks in flight -- measured the same 7.7-7.9 ms and was dropped.)
 template <int K>
 __device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint32_t &sb, const float *base, float &v) {
     asm volatile(
-        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r, i;\n .reg .b64 a;\n"
         " and.b32 t, %2, %5;\n"
         " setp.ne.u32 p, t, 0;\n"
         " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
         " and.b32 r, bal, %3;\n"
         " popc.b32 r, r;\n"
-        " add.u32 r, r, %1;\n"
+        " add.u32 i, r, %1;\n"
         " mov.f32 %0, 0f00000000;\n"
-        " mad.wide.u32 a, r, 4, %4;\n"
+        " mad.wide.u32 a, i, 4, %4;\n"
         " @p ld.global.nc.f32 %0, [a];\n"
-        " popc.b32 t, bal;\n"
+        " selp.u32 t, 1, 0, p;\n"
+        " add.u32 t, t, r;\n"
+        " shfl.sync.idx.b32 t, t, 31, 31, 0xffffffff;\n"
         " add.u32 %1, %1, t;\n}"
         : "=f"(v), "+r"(sb)
         : "r"(mask), "r"(lt), "l"(base), "n"(1u << K)
@@ -1120,17 +1148,19 @@ __device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint32_t
 template <int K>
 __device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint32_t &sb, const double *base, double &v) {
     asm volatile(
-        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r, i;\n .reg .b64 a;\n"
         " and.b32 t, %2, %5;\n"
         " setp.ne.u32 p, t, 0;\n"
         " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
         " and.b32 r, bal, %3;\n"
         " popc.b32 r, r;\n"
-        " add.u32 r, r, %1;\n"
+        " add.u32 i, r, %1;\n"
         " mov.f64 %0, 0d0000000000000000;\n"
-        " mad.wide.u32 a, r, 8, %4;\n"
+        " mad.wide.u32 a, i, 8, %4;\n"
         " @p ld.global.nc.f64 %0, [a];\n"
-        " popc.b32 t, bal;\n"
+        " selp.u32 t, 1, 0, p;\n"
+        " add.u32 t, t, r;\n"
+        " shfl.sync.idx.b32 t, t, 31, 31, 0xffffffff;\n"
         " add.u32 %1, %1, t;\n}"
         : "=d"(v), "+r"(sb)
         : "r"(mask), "r"(lt), "l"(base), "n"(1u << K)
@@ -1154,18 +1184,20 @@ __device__ __forceinline__ void gather_slots(std::integer_sequence<int, K...>, u
 __device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t lt, uint32_t &ob, int32_t *out_col,
                                           float *out_val, int32_t col, float val) {
     asm volatile(
-        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r, i;\n .reg .b64 a;\n"
         " and.b32 t, %1, %2;\n"
         " setp.ne.u32 p, t, 0;\n"
         " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
         " and.b32 r, bal, %3;\n"
         " popc.b32 r, r;\n"
-        " add.u32 r, r, %0;\n"
-        " mad.wide.u32 a, r, 4, %4;\n"
+        " add.u32 i, r, %0;\n"
+        " mad.wide.u32 a, i, 4, %4;\n"
         " @p st.global.b32 [a], %6;\n"
-        " mad.wide.u32 a, r, 4, %5;\n"
+        " mad.wide.u32 a, i, 4, %5;\n"
         " @p st.global.f32 [a], %7;\n"
-        " popc.b32 t, bal;\n"
+        " selp.u32 t, 1, 0, p;\n"
+        " add.u32 t, t, r;\n"
+        " shfl.sync.idx.b32 t, t, 31, 31, 0xffffffff;\n"
         " add.u32 %0, %0, t;\n}"
         : "+r"(ob)
         : "r"(mask), "r"(nz), "r"(lt), "l"(out_col), "l"(out_val), "r"(col), "f"(val)
@@ -1174,18 +1206,20 @@ __device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t l
 __device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t lt, uint32_t &ob, int32_t *out_col,
                                           double *out_val, int32_t col, double val) {
     asm volatile(
-        "{\n .reg .pred p;\n .reg .b32 t, bal, r;\n .reg .b64 a;\n"
+        "{\n .reg .pred p;\n .reg .b32 t, bal, r, i;\n .reg .b64 a;\n"
         " and.b32 t, %1, %2;\n"
         " setp.ne.u32 p, t, 0;\n"
         " vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
         " and.b32 r, bal, %3;\n"
         " popc.b32 r, r;\n"
-        " add.u32 r, r, %0;\n"
-        " mad.wide.u32 a, r, 4, %4;\n"
+        " add.u32 i, r, %0;\n"
+        " mad.wide.u32 a, i, 4, %4;\n"
         " @p st.global.b32 [a], %6;\n"
-        " mad.wide.u32 a, r, 8, %5;\n"
+        " mad.wide.u32 a, i, 8, %5;\n"
         " @p st.global.f64 [a], %7;\n"
-        " popc.b32 t, bal;\n"
+        " selp.u32 t, 1, 0, p;\n"
+        " add.u32 t, t, r;\n"
+        " shfl.sync.idx.b32 t, t, 31, 31, 0xffffffff;\n"
         " add.u32 %0, %0, t;\n}"
         : "+r"(ob)
         : "r"(mask), "r"(nz), "r"(lt), "l"(out_col), "l"(out_val), "r"(col), "d"(val)
@@ -1205,7 +1239,7 @@ __device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t l
 }
 
 template <int B, int TT, typename VT, typename IdxT>
-__global__ void __launch_bounds__(32) fill_from_union(const int64_t *__restrict__ in_rowptr,
+__global__ void __launch_bounds__(32, 12) fill_from_union(const int64_t *__restrict__ in_rowptr,
                                                       const int32_t *__restrict__ in_col,
                                                       const VT *__restrict__ in_val, int T_out, int halo, int64_t N,
                                                       const double *__restrict__ band_w, int b,
@@ -1224,12 +1258,33 @@ __global__ void __launch_bounds__(32) fill_from_union(const int64_t *__restrict_
     const uint32_t lt = (1u << lane) - 1u;
     const int64_t nblk = (N + 31) / 32;
     const int n_groups = (T_out + TT - 1) / TT;
-    const int64_t n_tasks = (int64_t)n_groups * nblk;
     const size_t stride = union_stride(qc);
-    for (int64_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const UnionTask ut = union_task(task, nblk, n_groups, true);
-        const int t0 = ut.g * TT;
-        const int64_t r0 = ut.blk * 32;
+    // a CTA keeps ONE group of output slices and walks the row blocks (grid = n_groups x walkers, like count_union):
+    // the weights of the group's outputs and their non-zero patterns are set up once, not per task
+    const int g = (int)(blockIdx.x % (unsigned)n_groups);
+    const int64_t walker = blockIdx.x / (unsigned)n_groups, n_walkers = gridDim.x / (unsigned)n_groups;
+    const int t0 = g * TT;
+    // weights of output tt on the j-th slot of its window (slot k = tt + j, lag l = B-1-j) -- as merge_rows_tiled
+    double w[TT][B];
+    uint32_t nz[TT];
+    uint32_t used_bits = 0;
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) {
+        nz[tt] = 0;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int l = B - 1 - j;
+            const int sl = halo + t0 + tt - l;
+            double wl = 0.0;
+            if (l < b && t0 + tt < T_out && sl >= 0) wl = band_w[(int64_t)(t0 + tt) * b + l];
+            w[tt][j] = wl;
+            if (wl != 0.0) nz[tt] |= 1u << (tt + j);
+        }
+        used_bits |= nz[tt];
+    }
+    for (int64_t blk = walker; blk < nblk; blk += n_walkers) {
+        const int64_t task = blk * n_groups + g;
+        const int64_t r0 = blk * 32;
         const uint8_t *const urec = utmp + UNION_HEADER + (size_t)task * stride;
         const uint32_t ul = reinterpret_cast<const uint16_t *>(urec)[lane];
         if (__any_sync(0xffffffffu, ul == 0xFFFFu)) continue;                 // overflowed record: fill_union_overflow
@@ -1263,35 +1318,13 @@ __global__ void __launch_bounds__(32) fill_from_union(const int64_t *__restrict_
                              : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        // weights of output tt on the j-th slot of its window (slot k = tt + j, lag l = B-1-j) -- as merge_rows_tiled
-        double w[TT][B];
-        uint32_t nz[TT];
-        bool used[NS];
-#pragma unroll
-        for (int k = 0; k < NS; ++k) used[k] = false;
-#pragma unroll
-        for (int tt = 0; tt < TT; ++tt) {
-            nz[tt] = 0;
-#pragma unroll
-            for (int j = 0; j < B; ++j) {
-                const int l = B - 1 - j;
-                const int sl = halo + t0 + tt - l;
-                double wl = 0.0;
-                if (l < b && t0 + tt < T_out && sl >= 0) wl = band_w[(int64_t)(t0 + tt) * b + l];
-                w[tt][j] = wl;
-                if (wl != 0.0) {
-                    nz[tt] |= 1u << (tt + j);
-                    used[tt + j] = true;
-                }
-            }
-        }
         // running positions: first entry of the block in every source slot, first output entry of the block
         // (IdxT = uint32_t when both tensors hold fewer than 2^32 entries: one IMAD.WIDE per address)
         IdxT sb[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             sb[k] = 0;
-            if (used[k]) sb[k] = (IdxT)in_rowptr[(int64_t)(halo + t0 - (B - 1) + k) * N + r0];
+            if (used_bits & (1u << k)) sb[k] = (IdxT)in_rowptr[(int64_t)(halo + t0 - (B - 1) + k) * N + r0];
         }
         IdxT ob[TT];
 #pragma unroll
@@ -1483,7 +1516,9 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
         const size_t csmem = smem + 16;                                                                          \
         TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));         \
         const int64_t n_groups = ceil_div(T_out, 4), n_blk = ceil_div(N, (int64_t)32);                           \
-        int64_t walkers = ((int64_t)sm_count() * per_sm) / n_groups;                                             \
+        int occ = 0;                                                                                             \
+        TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, csmem));                        \
+        int64_t walkers = ((int64_t)sm_count() * (occ > 0 ? occ : 1)) / n_groups;                                \
         if (walkers < 1) walkers = 1;                                                                            \
         if (walkers > n_blk) walkers = n_blk;                                                                    \
         kern<<<(unsigned)(n_groups * walkers), 32, csmem, st>>>(in_rowptr, in_col, nnz_in_host, T_out, halo, N,  \
@@ -1520,8 +1555,11 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
         TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));         \
         int occ = 0;                                                                                             \
         TMGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, usmem));                        \
-        int64_t ug = (int64_t)sm_count() * (occ > 0 ? occ : 1);                                                  \
-        if (ug > n_tasks) ug = n_tasks;                                                                          \
+        const int64_t n_groups = ceil_div(T_out, 4), n_blk = ceil_div(N, (int64_t)32);                           \
+        int64_t walkers = ((int64_t)sm_count() * (occ > 0 ? occ : 1)) / n_groups;                                \
+        if (walkers < 1) walkers = 1;                                                                            \
+        if (walkers > n_blk) walkers = n_blk;                                                                    \
+        const int64_t ug = n_groups * walkers;                                                                   \
         kern<<<(unsigned)ug, 32, usmem, st>>>(in_rowptr, in_col, in_val, T_out, halo, N, band_w, b,              \
                                               (const uint8_t *)ws, qc, out_rowptr, out_col, out_val);            \
         if (after_launch("fill_from_union")) return 1;                                                           \
@@ -1783,7 +1821,7 @@ size_t tmgcn_mtransform_sparse_ws_bytes(int T_out, int halo, int64_t N, int b, i
     if (!env_flag("TMGCN_MERGE_UNION", true) || !env_flag("TMGCN_MERGE_TT", true)) return 0;
     const double rows_in = (double)(T_out + halo) * (double)N;
     const double mean = (double)in_nnz / rows_in;
-    int qc = ((int)(mean * 5.0) + 8 + 3) & ~3;
+    int qc = ((int)(mean * 4.4) + 8 + 3) & ~3;
     if (qc < 16) qc = 16;
     if (qc > 96) qc = 96;
     const int64_t n_tasks = ceil_div(T_out, 4) * ceil_div(N, (int64_t)32);
