@@ -1,10 +1,10 @@
 #!/bin/bash
 # GPU call (1 GPU): full GPU test suite + the default bench line + smoke
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q > gpurun_out/r02_pytest5.log 2>&1; echo "pytest rc=$?"
+timeout 300 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest5.log 2>&1; echo "pytest rc=$?"
 tail -4 gpurun_out/r02_pytest5.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/r02_smoke.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo "bench rc=$?"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/r02_smoke.log
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/r02_bench_1gpu.json'))
