@@ -78,7 +78,8 @@ int tmgcn_mtransform_sparse_run(const int64_t *in_rowptr, const int32_t *in_col,
 /* The same two calls with a caller-owned workspace (tmgcn_mtransform_sparse_ws_bytes; 0 = not applicable, pass
  * NULL): the plan call records the union pattern of every (4 output slices x 32 rows) task in it and the run call
  * turns the record into values without merging again (about 2x faster; results are bit-identical).  The same
- * workspace, untouched in between, must be passed to both calls.  in_nnz = in_rowptr[(halo+T_out)*N]. */
+ * workspace, untouched in between, must be passed to both calls.  in_nnz = in_rowptr[(halo+T_out)*N].
+ * fp32 values only: with val_is_f64 the run call ignores the record and merges as tmgcn_mtransform_sparse_run does. */
 size_t tmgcn_mtransform_sparse_ws_bytes(int T_out, int halo, int64_t N, int b, int64_t in_nnz);
 int tmgcn_mtransform_sparse_plan_ws(const int64_t *in_rowptr, const int32_t *in_col, int T_out, int halo, int64_t N,
                                     const double *band_w, int b, int64_t *out_counts, void *ws, size_t ws_bytes,

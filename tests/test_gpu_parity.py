@@ -177,6 +177,43 @@ for b in (2, 5, 10, 24):
         assert outs[flag] == outs["0"], flag
 
 
+def test_mtransform_sparse_workspace_paths(tg):
+    """the union-list variant through the raw C ABI with hand-sized workspaces: a record depth that most rows
+    overflow (the run call must fall back to the merging fill), one that a few rows overflow (union fill + the
+    overflow launch), the library's own size, and no workspace at all -- same bits every time.  fp64 values: the
+    run call ignores the record (the union fill serves the fp32 layout only) and must still agree."""
+    import ctypes as C
+    from tmgcn_b200 import _lib, ops, synth
+    from tmgcn_b200.ops import _p, _stream
+    lib = _lib.load()
+    T, N, b = 14, 3000, 5
+    idx, val = synth.synth_coo(N, T, 3000, 0.8, seed=5)
+    band = tg.Band(tg.create_matrix_M(T, b))
+    w = band.device_weights(0, T, torch.float64)
+    n_tasks = ((T + 3) // 4) * ((N + 31) // 32)
+    for dt in (torch.float32, torch.float64):
+        A = tg.SliceCSR.from_coo(idx, val, T, N, dtype=dt)
+        ref = ops.mtransform_sparse(A, band)
+        own = int(lib.tmgcn_mtransform_sparse_ws_bytes(T, 0, N, b, A.nnz))
+        assert own > 256
+        for ws_bytes in (0, 256 + n_tasks * (64 + 8 * 192), 256 + n_tasks * (64 + 13 * 192), own):
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.col.device) if ws_bytes else None
+            counts = torch.empty(T * N, dtype=torch.int64, device=A.col.device)
+            _lib.check(lib.tmgcn_mtransform_sparse_plan_ws(_p(A.rowptr), _p(A.col), T, 0, N, _p(w), b, _p(counts),
+                                                           _p(ws), C.c_size_t(ws_bytes), _stream()))
+            rowptr = ops.exclusive_scan(counts)
+            assert torch.equal(rowptr, ref.rowptr), ws_bytes
+            col = torch.full((ref.nnz,), -7, dtype=torch.int32, device=A.col.device)
+            out = torch.full((ref.nnz,), float("nan"), dtype=dt, device=A.col.device)
+            _lib.check(lib.tmgcn_mtransform_sparse_run_ws(_p(A.rowptr), _p(A.col), _p(A.val), T, 0, N, _p(w), b,
+                                                          _p(rowptr), _p(col), _p(out), 1 if dt == torch.float64 else 0,
+                                                          _p(ws), C.c_size_t(ws_bytes), _stream()))
+            assert torch.equal(col, ref.col), ws_bytes
+            assert torch.equal(out, ref.val), ws_bytes
+            if ws is not None:
+                print("workspace", str(dt), ws_bytes, "overflowed records:", int(ws[:4].view(torch.int32).item()))
+
+
 def test_mtransform_sparse_zero_weight_and_cancellation(tg):
     """explicit zeros inside the band drop the source slice (nonzero(M[:, j]), ref: read_data.py:216);
     sums that cancel to 0.0 stay stored (coalesce never prunes)."""

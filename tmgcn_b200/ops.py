@@ -274,7 +274,7 @@ def mtransform_sparse(csr: SliceCSR, band: Band, t0: int = 0, t1: Optional[int] 
     dev = csr.rowptr.device
     counts = torch.empty(T_out * N, dtype=torch.int64, device=dev)
     # workspace of the union-list variant (0 bytes = not applicable: the fill pass merges again)
-    ws_bytes = int(lib.tmgcn_mtransform_sparse_ws_bytes(T_out, halo, N, band.b, csr.nnz))
+    ws_bytes = 0 if f64 else int(lib.tmgcn_mtransform_sparse_ws_bytes(T_out, halo, N, band.b, csr.nnz))   # fp32 layout only
     ws = None
     if ws_bytes:
         try:
