@@ -13,6 +13,14 @@ dev = torch.device("cuda", 0)
 idx, val = synth.synth_coo(N, T, 3 * N, 0.85, seed=11, device="cpu")
 band = tg.Band(tg.create_matrix_M(T, b))
 At = ops.mtransform_sparse(tg.SliceCSR.from_coo(idx, val, T, N), band)
+# the union-list kernels' overflow paths: a hub row (its block misses the staging pool -> fill_union_overflow) ...
+hub = torch.stack([torch.randint(0, T, (4000,)), torch.full((4000,), 7), torch.randint(0, N, (4000,))])
+Ch = torch.sparse_coo_tensor(torch.cat([idx, hub], 1), torch.cat([val, torch.rand(4000, dtype=torch.float64)]),
+                             (T, N, N)).coalesce()
+for dt in (torch.float32, torch.float64):
+    o = ops.mtransform_sparse(tg.SliceCSR.from_coo(Ch._indices(), Ch._values(), T, N, dtype=dt), band)
+    print("hub", dt, o.nnz, float(o.val.double().sum()))
+del Ch, hub, o
 g = torch.Generator().manual_seed(3)
 H = torch.rand(T, N, F, generator=g).to(dev)
 W = (torch.randn(F, F, generator=g) / F ** 0.5).to(dev)
