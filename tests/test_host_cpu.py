@@ -38,6 +38,32 @@ def test_library_exports_every_declared_symbol():
     assert lib.tmgcn_csr_transpose_ws_bytes(10, 100, 1) == 100 * 16 + 10 * 8
 
 
+def test_sparse_transform_workspace_size_is_host_arithmetic():
+    """tmgcn_mtransform_sparse_ws_bytes needs no GPU: 0 where the union-list variant does not apply, otherwise a
+    256-byte header + one fixed-stride record (64 B of row lengths + 192 B per union entry of depth) per
+    (4 output slices x 32 rows) task, the depth a multiple of 4 that grows with the mean row length."""
+    from tmgcn_b200 import _lib
+    lib = _lib.load()
+    f = lib.tmgcn_mtransform_sparse_ws_bytes
+    N, T = 100_000, 32
+    assert f(3, 0, N, 10, 10 * N * 3) == 0              # fewer than 4 output slices
+    assert f(T, 0, N, 13, 10 * N * T) == 0              # band wider than the 16-bit hit masks allow
+    assert f(T, 0, N, 10, 0) == 0                       # empty input
+    sizes = []
+    for mean in (1, 3, 11, 30):
+        b = int(f(T, 0, N, 10, mean * N * T))
+        n_tasks = (T // 4) * ((N + 31) // 32)
+        assert b > 256 and (b - 256) % n_tasks == 0
+        per_task = (b - 256) // n_tasks
+        assert (per_task - 64) % 192 == 0
+        depth = (per_task - 64) // 192
+        assert depth % 4 == 0 and 16 <= depth <= 96 and depth >= 1.5 * mean
+        sizes.append(b)
+    assert sizes == sorted(sizes)
+    # a halo lengthens the input, not the task list
+    assert int(f(T, 9, N, 10, 11 * N * (T + 9))) == sizes[2]
+
+
 def test_product_fails_loudly_without_gpu():
     import tmgcn_b200
     if torch.cuda.is_available():
