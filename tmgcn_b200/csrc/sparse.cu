@@ -1166,15 +1166,6 @@ __device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint32_t
         : "r"(mask), "r"(lt), "l"(base), "n"(1u << K)
         : "memory");
 }
-// generic-index version (tensors with 2^32 entries or more)
-template <int K, typename VT>
-__device__ __forceinline__ void slot_gather(uint32_t mask, uint32_t lt, uint64_t &sb, const VT *base, VT &v) {
-    const bool bit = (mask & (1u << K)) != 0;
-    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-    v = (VT)0;
-    if (bit) v = base[sb + (uint64_t)__popc(bal & lt)];
-    sb += (uint64_t)__popc(bal);
-}
 template <typename VT, typename IdxT, int... K>
 __device__ __forceinline__ void gather_slots(std::integer_sequence<int, K...>, uint32_t mask, uint32_t lt,
                                              IdxT (&sb)[sizeof...(K)], const VT *base, VT (&v)[sizeof...(K)]) {
@@ -1225,19 +1216,6 @@ __device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t l
         : "r"(mask), "r"(nz), "r"(lt), "l"(out_col), "l"(out_val), "r"(col), "d"(val)
         : "memory");
 }
-template <typename VT>
-__device__ __forceinline__ void slot_emit(uint32_t mask, uint32_t nz, uint32_t lt, uint64_t &ob, int32_t *out_col,
-                                          VT *out_val, int32_t col, VT val) {
-    const bool pres = (mask & nz) != 0;
-    const uint32_t bal = __ballot_sync(0xffffffffu, pres);
-    if (pres) {
-        const uint64_t pos = ob + (uint64_t)__popc(bal & lt);
-        out_col[pos] = col;
-        out_val[pos] = val;
-    }
-    ob += (uint64_t)__popc(bal);
-}
-
 template <int B, int TT, typename VT, typename IdxT>
 __global__ void __launch_bounds__(32, 12) fill_from_union(const int64_t *__restrict__ in_rowptr,
                                                       const int32_t *__restrict__ in_col,
@@ -1319,7 +1297,7 @@ __global__ void __launch_bounds__(32, 12) fill_from_union(const int64_t *__restr
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         // running positions: first entry of the block in every source slot, first output entry of the block
-        // (IdxT = uint32_t when both tensors hold fewer than 2^32 entries: one IMAD.WIDE per address)
+        // (IdxT = uint32_t: the variant serves tensors with fewer than 2^32 entries; one IMAD.WIDE per address)
         IdxT sb[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -1545,12 +1523,14 @@ static int launch_merge(const int64_t *in_rowptr, const int32_t *in_col, const V
                 TMGCN_CUDA(cudaMemcpyAsync(&nnz_io[1], out_rowptr + (int64_t)T_out * N, sizeof(int64_t),
                                            cudaMemcpyDeviceToHost, st));
                 TMGCN_CUDA(cudaStreamSynchronize(st));
-                union_fill = (int64_t)n_over * 20 <= n_tasks;               // mostly overflowed records: merge again
                 idx32 = nnz_io[0] < ((int64_t)1 << 32) && nnz_io[1] < ((int64_t)1 << 32);
+                // mostly overflowed records: merge again.  Tensors with 2^32 entries or more: the merging kernels
+                // (the lane-per-entry walk keeps its running positions in 32 bits).
+                union_fill = (int64_t)n_over * 20 <= n_tasks && idx32;
             }
 #define TMGCN_UNION_FILL(BB)                                                                                     \
     if (b <= BB) {                                                                                               \
-        auto kern = idx32 ? fill_from_union<BB, 4, VT, uint32_t> : fill_from_union<BB, 4, VT, uint64_t>;         \
+        auto kern = fill_from_union<BB, 4, VT, uint32_t>;                                                        \
         const size_t usmem = (size_t)qc * 256;                                                                   \
         TMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));         \
         int occ = 0;                                                                                             \
